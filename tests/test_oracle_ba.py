@@ -1,0 +1,216 @@
+"""Pins the bundle-adjustment half of the CPU oracle.
+
+Golden vectors:
+  E2E-1  docs/source/installation.rst:185-193 — simple_bundle_adjuster on the raw file, exact solve
+  E2E-1' docs/source/solving_faqs.rst:72-77   — bundle_adjuster (= BASELINE.json configs[0]) after
+         BALProblem::Normalize(), exact (SPARSE_SCHUR) solve
+Every printed digit of both per-iteration tables must be reproduced.
+"""
+import numpy as np
+import pytest
+
+# iter: (cost, cost_change, |gradient|_inf, |step|, tr_ratio, tr_radius) as printed by the reference
+G1 = [
+    ("4.185660e+06", "0.00e+00", "1.09e+08", "0.00e+00", "0.00e+00", "1.00e+04"),
+    ("1.062590e+05", "4.08e+06", "8.99e+06", None, "9.82e-01", "3.00e+04"),  # |step| printed 0.00 by that version
+    ("4.992817e+04", "5.63e+04", "8.32e+06", "3.19e+02", "6.52e-01", "3.09e+04"),
+    ("1.899774e+04", "3.09e+04", "1.60e+06", "1.24e+02", "9.77e-01", "9.26e+04"),
+    ("1.808729e+04", "9.10e+02", "3.97e+05", "6.39e+01", "9.51e-01", "2.78e+05"),
+    ("1.803399e+04", "5.33e+01", "1.48e+04", "1.23e+01", "9.99e-01", "8.33e+05"),
+    ("1.803390e+04", "9.02e-02", "6.35e+01", "8.00e-01", "1.00e+00", "2.50e+06"),
+]
+G2 = [
+    ("4.185660e+06", "0.00e+00", "2.16e+07", "0.00e+00", "0.00e+00", "1.00e+04"),
+    ("1.980525e+05", "3.99e+06", "5.34e+06", "2.40e+03", "9.60e-01", "3.00e+04"),
+    ("5.086543e+04", "1.47e+05", "2.11e+06", "1.01e+03", "8.22e-01", "4.09e+04"),
+    ("1.859667e+04", "3.23e+04", "2.87e+05", "2.64e+02", "9.85e-01", "1.23e+05"),
+    ("1.803857e+04", "5.58e+02", "2.69e+04", "8.66e+01", "9.93e-01", "3.69e+05"),
+    ("1.803391e+04", "4.66e+00", "3.11e+02", "1.02e+01", "1.00e+00", "1.11e+06"),
+]
+# Restatement-derived: ITERATIVE_SCHUR + SCHUR_JACOBI, eta 1e-2 on normalised C16
+G3 = [  # (CG iterations, cost, |step|, tr_ratio, accepted, radius after)
+    (5, "7.046534e+04", "2.06e+03", "9.94e-01", 1, "3.00e+04"),
+    (16, "1.235384e+05", "1.95e+03", "-1.06e+00", 0, "1.50e+04"),
+    (23, "5.934463e+04", "1.27e+03", "2.28e-01", 1, "1.29e+04"),
+    (23, "1.957980e+04", "2.87e+02", "9.83e-01", 1, "3.88e+04"),
+    (15, "1.834333e+04", "2.71e+02", "8.39e-01", 1, "5.62e+04"),
+]
+
+
+def _program(oracle, bal, **kw):
+    return oracle.BaProgram(bal.C, bal.P, bal.cam_idx, bal.pt_idx, bal.obs, **kw)
+
+
+def _check_table(recs, table):
+    assert len(recs) >= len(table)
+    for rec, row in zip(recs, table):
+        got = ("%.6e" % rec["cost"], "%.2e" % rec["cost_change"], "%.2e" % rec["gradient_max_norm"],
+               "%.2e" % rec["step_norm"], "%.2e" % rec["tr_ratio"], "%.2e" % rec["tr_radius"])
+        for g, want in zip(got, row):
+            if want is not None:
+                assert g == want, (rec["iteration"], got, row)
+
+
+def test_header_and_initial_cost(oracle, c16_raw):
+    assert (c16_raw.C, c16_raw.P, c16_raw.N) == (16, 22106, 83718)
+    prog = _program(oracle, c16_raw)
+    state = prog.state_from_parameters(c16_raw.cameras, c16_raw.points)
+    ok, cost, _, _ = prog.evaluate(state, want_gradient=False, want_jacobian=False)
+    assert ok and "%.6e" % cost == "4.185660e+06"  # installation.rst:214
+
+
+def test_normalize_facts(oracle, c16_raw, c16):
+    """bal_problem.cc:249-292 on this file: upper median via nth_element, MAD, scale."""
+    pts = c16_raw.points.reshape(-1, 3)
+    med = np.array([np.sort(pts[:, i])[len(pts) // 2] for i in range(3)])
+    assert np.allclose(med, [1.65442666, 3.78860467, -29.72038654], atol=5e-9)
+    l1 = np.abs(pts - med).sum(axis=1)
+    mad = np.sort(l1)[len(l1) // 2]
+    assert abs(mad - 22.608061669690585) < 1e-9
+    scale = 100.0 / mad
+    assert np.allclose(c16.points.reshape(-1, 3), scale * (pts - med), rtol=1e-13, atol=1e-12)
+    # the cost is invariant under Normalize()
+    prog = _program(oracle, c16)
+    state = prog.state_from_parameters(c16.cameras, c16.points)
+    ok, cost, _, _ = prog.evaluate(state, want_gradient=False, want_jacobian=False)
+    assert ok and "%.6e" % cost == "4.185660e+06"
+
+
+def test_program_ordering(oracle):
+    """reorder_program.cc:247-273 (first-use order inside each group) and :278-359 (rows bucketed by
+    e block, each bucket filled back to front)."""
+    cam = [2, 0, 2, 1, 0, 1]
+    pt = [1, 1, 0, 2, 0, 2]
+    obs = np.arange(12, dtype=float)
+    prog = oracle.BaProgram(3, 3, cam, pt, obs)
+    assert list(prog.camera_of_fblock) == [2, 0, 1]
+    assert list(prog.point_of_eblock) == [1, 0, 2]
+    # e block 0 = point 1: observations 0,1 -> reversed (1,0); e block 1 = point 0: obs 2,4 -> (4,2); ...
+    assert list(prog.obs_of_row) == [1, 0, 4, 2, 5, 3]
+    assert list(prog.row_pt) == [0, 0, 1, 1, 2, 2]
+    assert list(prog.row_cam) == [1, 0, 1, 0, 2, 2]
+    assert np.allclose(prog.row_obs.reshape(-1, 2)[0], obs.reshape(-1, 2)[1])
+
+
+@pytest.mark.parametrize("nt", [1, 8])
+def test_trace_G1_raw_exact_solve(oracle, c16_raw, nt):
+    prog = _program(oracle, c16_raw)
+    state = prog.state_from_parameters(c16_raw.cameras, c16_raw.points)
+    o = prog.default_options()
+    o.linear_solver = 1
+    o.max_num_iterations = 6
+    o.num_threads = nt
+    _, recs, _ = prog.solve(state, o)
+    _check_table(recs, G1)
+
+
+@pytest.mark.parametrize("nt", [1, 8])
+def test_trace_G2_config0(oracle, c16, nt):
+    prog = _program(oracle, c16)
+    state = prog.state_from_parameters(c16.cameras, c16.points)
+    o = prog.default_options()
+    o.linear_solver = 1
+    o.num_threads = nt
+    _, recs, _ = prog.solve(state, o)
+    _check_table(recs, G2)
+    assert all(r["step_is_successful"] for r in recs)
+
+
+@pytest.mark.parametrize("nt", [1, 8])
+def test_trace_G3_iterative_schur(oracle, c16, nt):
+    prog = _program(oracle, c16)
+    state = prog.state_from_parameters(c16.cameras, c16.points)
+    o = prog.default_options()
+    o.num_threads = nt
+    _, recs, _ = prog.solve(state, o)
+    assert len(recs) == 6
+    for rec, (its, cost, step, ratio, ok, radius) in zip(recs[1:], G3):
+        assert int(rec["ls_iterations"]) == its
+        assert "%.6e" % rec["cost"] == cost
+        assert "%.2e" % rec["step_norm"] == step
+        assert "%.2e" % rec["tr_ratio"] == ratio
+        assert int(rec["step_is_successful"]) == ok
+        assert "%.2e" % rec["tr_radius"] == radius
+
+
+def test_jacobian_against_finite_differences(oracle, c16):
+    prog = _program(oracle, c16)
+    state = prog.state_from_parameters(c16.cameras, c16.points)
+    ok, cost, res, grad = prog.evaluate(state)
+    J = prog.jacobian()
+    rng = np.random.RandomState(0)
+    d = rng.randn(prog.num_parameters)
+    d /= np.linalg.norm(d)
+    h = 1e-6
+    _, _, rp, _ = prog.evaluate(state + h * d, want_gradient=False, want_jacobian=False)
+    _, _, rm, _ = prog.evaluate(state - h * d, want_gradient=False, want_jacobian=False)
+    # evaluate(..., want_jacobian=False) leaves the stored Jacobian untouched
+    fd = (rp - rm) / (2 * h)
+    jd = J.right_multiply(d)
+    assert np.linalg.norm(fd - jd) / np.linalg.norm(jd) < 1e-6
+    assert np.allclose(J.left_multiply(res), grad, rtol=1e-12, atol=1e-6)
+    assert abs(0.5 * res @ res - cost) / cost < 1e-14
+
+
+def test_jacobian_layout(oracle, c16):
+    """E cells first (6 doubles each, row order), then F cells (18 each): block_jacobian_writer.cc:68-167."""
+    prog = _program(oracle, c16)
+    state = prog.state_from_parameters(c16.cameras, c16.points)
+    prog.evaluate(state)
+    J = prog.jacobian()
+    v = J.values()
+    N = prog.N
+    assert v.size == 24 * N
+    x = np.zeros(prog.num_parameters)
+    j = int(prog.row_pt[7])
+    x[3 * j] = 1.0
+    y = J.right_multiply(x)
+    assert y[14] == v[6 * 7 + 0] and y[15] == v[6 * 7 + 3]
+    x[:] = 0
+    k = int(prog.row_cam[7])
+    x[3 * prog.P + 9 * k + 4] = 1.0
+    y = J.right_multiply(x)
+    assert y[14] == v[6 * N + 18 * 7 + 4] and y[15] == v[6 * N + 18 * 7 + 13]
+
+
+def test_theta_zero_branch(oracle):
+    """rotation.h:873,905-927: exactly zero rotation uses R = I + [w]x, which also defines the derivative."""
+    cams = np.array([[0, 0, 0, 0.1, -0.2, -5.0, 800.0, 1e-7, 1e-13]], dtype=float)
+    pts = np.array([[0.3, -0.4, 1.5], [1.0, 0.5, 2.0]])
+    prog = oracle.BaProgram(1, 2, [0, 0], [0, 1], np.array([10.0, -3.0, 5.0, 8.0]))
+    state = prog.state_from_parameters(cams.ravel(), pts.ravel())
+    ok, cost, res, grad = prog.evaluate(state)
+    assert ok
+    J = prog.jacobian()
+    # d/d(omega) at omega = 0 of  X + omega x X  is -[X]x; check through finite differences of the
+    # *linearised* model: r(omega) with tiny omega uses the Rodrigues branch and agrees to O(|omega|^2)
+    h = 1e-7
+    for a in range(3):
+        d = np.zeros(prog.num_parameters)
+        d[3 * prog.P + a] = 1.0
+        _, _, rp, _ = prog.evaluate(state + h * d, want_gradient=False, want_jacobian=False)
+        fd = (rp - res) / h
+        assert np.allclose(J.right_multiply(d), fd, rtol=1e-5, atol=1e-4)
+
+
+def test_huber_corrector(oracle, c16):
+    """loss_function.cc:52-66 + corrector.cc:41-155: cost = 0.5 rho(s); with HuberLoss(1.0) the
+    outlier region has rho'' < 0 so J and r are both scaled by sqrt(rho')."""
+    plain = _program(oracle, c16)
+    robust = _program(oracle, c16, use_huber=True, huber_a=1.0)
+    state = plain.state_from_parameters(c16.cameras, c16.points)
+    _, cost0, r0, g0 = plain.evaluate(state)
+    _, cost1, r1, g1 = robust.evaluate(state)
+    s = (r0.reshape(-1, 2) ** 2).sum(axis=1)
+    rho = np.where(s > 1.0, 2.0 * np.sqrt(s) - 1.0, s)
+    assert abs(cost1 - 0.5 * rho.sum()) / cost1 < 1e-13
+    w = np.where(s > 1.0, np.sqrt(1.0 / np.sqrt(np.maximum(s, 1e-300))), 1.0)
+    assert np.allclose(r1.reshape(-1, 2), r0.reshape(-1, 2) * w[:, None], rtol=1e-13, atol=0)
+    v0 = plain.jacobian().values()
+    v1 = robust.jacobian().values()
+    N = plain.N
+    assert np.allclose(v1[:6 * N].reshape(N, 6), v0[:6 * N].reshape(N, 6) * w[:, None], rtol=1e-13)
+    assert np.allclose(v1[6 * N:].reshape(N, 18), v0[6 * N:].reshape(N, 18) * w[:, None], rtol=1e-13)
+    # gradient of the robustified cost: sum rho'(s) J'r
+    assert np.allclose(g1, plain.jacobian().left_multiply((r0.reshape(-1, 2) * (w * w)[:, None]).ravel()),
+                       rtol=1e-10, atol=1e-6)

@@ -1,0 +1,240 @@
+"""Pins the CPU oracle against the reference's own known-answer fixtures.
+
+Mirrors the reference tests that hold these vectors:
+  schur_eliminator_test.cc:82-177        eliminator vs dense R - Q'PQ           (1e-14 rel)
+  implicit_schur_complement_test.cc:119-216  implicit S columns / rhs / back-substitution vs eliminator
+  partitioned_matrix_view_test.cc:103-272    E/F products and block diagonals vs dense
+  iterative_schur_complement_solver_test.cc:76-149, schur_complement_solver_test.cc:151-320
+                                          solver solution vs DENSE_QR (numpy lstsq here)
+  block_sparse_matrix_test.cc:191-674    SpMV / SquaredColumnNorm / ScaleColumns
+plus the printed S, r, S\\r, A\\b, x, x_D of linear_least_squares_problems.cc.
+"""
+import numpy as np
+import pytest
+
+from tests.golden.llsq_fixtures import FIXTURES, dense, num_cols_e
+
+IDS = [0, 1, 2, 3, 4, 5, 6]
+
+
+def make(oracle, fx):
+    return oracle.BlockSparseMatrix(fx["col_sizes"], fx["row_sizes"], fx["row_cells"], fx["values"])
+
+
+def elim_blocks(pid, fx):
+    return 1 if pid == 0 else fx["num_eliminate_blocks"]
+
+
+def dense_schur(A, b, D, ne):
+    """H = A'A + D^2; S = R - Q' P^-1 Q; rhs = g_f - Q' P^-1 g_e  (schur_eliminator_test.cc:82-121)."""
+    H = A.T @ A + (np.diag(D * D) if D is not None else 0.0)
+    g = A.T @ b
+    P, Q, R = H[:ne, :ne], H[:ne, ne:], H[ne:, ne:]
+    Pinv = np.linalg.inv(P)
+    S = R - Q.T @ Pinv @ Q
+    rhs = g[ne:] - Q.T @ Pinv @ g[:ne]
+    return S, rhs, H, g
+
+
+@pytest.mark.parametrize("pid", IDS)
+def test_transcription_matches_printed_normal_matrix(pid):
+    fx = FIXTURES[pid]
+    if "AtA" not in fx:
+        pytest.skip("no printed A'A for this fixture")
+    A = dense(fx)
+    assert np.allclose(A.T @ A, np.array(fx["AtA"], dtype=float), atol=1e-12)
+
+
+@pytest.mark.parametrize("pid", IDS)
+@pytest.mark.parametrize("nt", [1, 4])
+def test_block_sparse_products(oracle, pid, nt):
+    fx = FIXTURES[pid]
+    A = dense(fx)
+    M = make(oracle, fx)
+    rng = np.random.RandomState(pid)
+    x = rng.randn(A.shape[1])
+    y = rng.randn(A.shape[0])
+    assert np.allclose(M.right_multiply(x, nt), A @ x, rtol=0, atol=1e-12)
+    assert np.allclose(M.left_multiply(y, nt), A.T @ y, rtol=0, atol=1e-12)
+    assert np.allclose(M.squared_column_norm(nt), (A * A).sum(axis=0), rtol=1e-14, atol=0)
+    s = rng.rand(A.shape[1]) + 0.5
+    M.scale_columns(s, nt)
+    assert np.allclose(M.right_multiply(x, nt), (A * s) @ x, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("pid", IDS)
+@pytest.mark.parametrize("nt", [1, 2, 4, 8])
+def test_partitioned_view(oracle, pid, nt):
+    fx = FIXTURES[pid]
+    ne_blocks = elim_blocks(pid, fx)
+    A = dense(fx)
+    ne = int(sum(fx["col_sizes"][:ne_blocks]))
+    E, F = A[:, :ne], A[:, ne:]
+    M = make(oracle, fx)
+    rng = np.random.RandomState(10 + pid)
+    xe, xf, y = rng.randn(ne), rng.randn(A.shape[1] - ne), rng.randn(A.shape[0])
+    assert np.allclose(M.pmv(ne_blocks, 0, xe, A.shape[0], nt), E @ xe, atol=1e-12)
+    assert np.allclose(M.pmv(ne_blocks, 1, xf, A.shape[0], nt), F @ xf, atol=1e-12)
+    assert np.allclose(M.pmv(ne_blocks, 2, y, ne, nt), E.T @ y, atol=1e-12)
+    assert np.allclose(M.pmv(ne_blocks, 3, y, A.shape[1] - ne, nt), F.T @ y, atol=1e-12)
+    # block diagonals
+    ete = M.block_diagonal(ne_blocks, 0, nt)
+    p = 0
+    c0 = 0
+    for s in fx["col_sizes"][:ne_blocks]:
+        blk = (E.T @ E)[c0:c0 + s, c0:c0 + s]
+        assert np.allclose(ete[p:p + s * s].reshape(s, s), blk, atol=1e-12)
+        p += s * s
+        c0 += s
+    ftf = M.block_diagonal(ne_blocks, 1, nt)
+    p = 0
+    c0 = 0
+    for s in fx["col_sizes"][ne_blocks:]:
+        blk = (F.T @ F)[c0:c0 + s, c0:c0 + s]
+        assert np.allclose(ftf[p:p + s * s].reshape(s, s), blk, atol=1e-12)
+        p += s * s
+        c0 += s
+
+
+@pytest.mark.parametrize("pid", [0, 2, 4, 5, 6])
+@pytest.mark.parametrize("use_D", [False, True])
+@pytest.mark.parametrize("nt", [1, 4])
+@pytest.mark.parametrize("force_dynamic", [0, 1])
+def test_schur_eliminator_vs_dense(oracle, pid, use_D, nt, force_dynamic):
+    fx = FIXTURES[pid]
+    if pid in (4, 6) and not use_D:
+        pytest.skip("rank deficient without the diagonal (reference note :545-547)")
+    ne_blocks = elim_blocks(pid, fx)
+    A = dense(fx)
+    ne = int(sum(fx["col_sizes"][:ne_blocks]))
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float) if use_D else None
+    S, rhs, H, g = dense_schur(A, b, D, ne)
+    M = make(oracle, fx)
+    lhs, r = M.schur_eliminate(ne_blocks, b, D, nt=nt, force_dynamic=force_dynamic)
+    # the eliminator fills the upper block triangle only
+    lhs_full = np.triu(lhs) + np.triu(lhs, 1).T
+    fsizes = fx["col_sizes"][ne_blocks:]
+    # inside diagonal blocks both triangles are written; check them unsymmetrised too
+    c0 = 0
+    for s in fsizes:
+        assert np.allclose(lhs[c0:c0 + s, c0:c0 + s], S[c0:c0 + s, c0:c0 + s], rtol=1e-13, atol=1e-13 * abs(S).max())
+        c0 += s
+    assert np.linalg.norm(lhs_full - S) / np.linalg.norm(S) < 1e-14 * 10
+    assert np.linalg.norm(r - rhs) / np.linalg.norm(rhs) < 1e-13
+    # back substitution: full solution of the regularised normal equations
+    z = np.linalg.solve(S, rhs)
+    sol = M.schur_back_substitute(ne_blocks, b, D, z, nt=nt, force_dynamic=force_dynamic)
+    expect = np.linalg.solve(H, g)
+    assert np.allclose(sol[:ne], expect[:ne], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("pid", [2, 5])
+def test_printed_schur_complement(oracle, pid):
+    """KAT-1 / KAT-2: printed S, r, S\\r, A\\b (4 decimals) for D = 0."""
+    fx = FIXTURES[pid]
+    M = make(oracle, fx)
+    b = np.array(fx["b"], dtype=float)
+    lhs, r = M.schur_eliminate(fx["num_eliminate_blocks"], b, None)
+    S = np.triu(lhs) + np.triu(lhs, 1).T
+    assert np.allclose(S, np.array(fx["S"]), atol=6e-5)
+    assert np.allclose(r, np.array(fx["r"]), atol=6e-5)
+    z = np.linalg.solve(S, r)
+    assert np.allclose(z, np.array(fx["S_solve_r"]), atol=6e-5)
+    x, its, term = M.linear_solve(fx["num_eliminate_blocks"], b, None, solver=1)
+    assert term == 0
+    assert np.allclose(x, np.array(fx["x"]), atol=1.1e-4)
+
+
+def test_problem0_known_solutions(oracle):
+    """KAT-3: x = [2,3]; with D = [1,2]: x_D = [1.78448275, 2.82327586]."""
+    fx = FIXTURES[0]
+    M = make(oracle, fx)
+    b = np.array(fx["b"], dtype=float)
+    x, _, term = M.linear_solve(1, b, None, solver=1)
+    assert term == 0 and np.allclose(x, fx["x"], atol=1e-12)
+    xd, _, term = M.linear_solve(1, b, np.array(fx["D"], dtype=float), solver=1)
+    assert term == 0 and np.allclose(xd, fx["x_D"], atol=5e-9)
+    xi, its, term = M.linear_solve(1, b, np.array(fx["D"], dtype=float), solver=0, r_tolerance=1e-12, max_iter=50)
+    assert term == 0 and np.allclose(xi, fx["x_D"], atol=5e-9)
+
+
+@pytest.mark.parametrize("pid", [2, 4, 5, 6])
+@pytest.mark.parametrize("use_D", [False, True])
+@pytest.mark.parametrize("force_dynamic", [0, 1])
+def test_implicit_schur_complement(oracle, pid, use_D, force_dynamic):
+    """implicit_schur_complement_test.cc:119-216: columns of S, rhs and back-substitution (1e-14 abs there)."""
+    fx = FIXTURES[pid]
+    if pid in (4, 6) and not use_D:
+        pytest.skip("rank deficient without the diagonal")
+    ne_blocks = fx["num_eliminate_blocks"]
+    A = dense(fx)
+    ne = num_cols_e(fx)
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float) if use_D else None
+    S, rhs, H, g = dense_schur(A, b, D, ne)
+    M = make(oracle, fx)
+    isc = oracle.ImplicitSchur(M, ne_blocks, want_ftf=True, force_dynamic=force_dynamic)
+    isc.init(D, b)
+    nf = A.shape[1] - ne
+    scale = abs(S).max()
+    for i in range(nf):
+        e = np.zeros(nf)
+        e[i] = 1.0
+        assert np.allclose(isc.right_multiply(e), S[:, i], rtol=0, atol=1e-13 * scale)
+    assert np.allclose(isc.rhs(), rhs, rtol=0, atol=1e-13 * max(1.0, abs(rhs).max()))
+    z = np.linalg.solve(S, rhs)
+    sol = isc.back_substitute(z)
+    expect = np.linalg.solve(H, g)
+    assert np.allclose(sol, expect, rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("pid", [2, 3, 5])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+@pytest.mark.parametrize("use_D", [False, True])
+def test_iterative_schur_vs_dense_qr(oracle, pid, precond, use_D):
+    """iterative_schur_complement_solver_test.cc:76-115 (r_tolerance 1e-12, compare with DENSE_QR at 1e-14..)."""
+    fx = FIXTURES[pid]
+    A = dense(fx)
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float) if use_D else None
+    Aaug = np.vstack([A, np.diag(D)]) if use_D else A
+    baug = np.concatenate([b, np.zeros(A.shape[1])]) if use_D else b
+    expect = np.linalg.lstsq(Aaug, baug, rcond=None)[0]
+    M = make(oracle, fx)
+    x, its, term = M.linear_solve(fx["num_eliminate_blocks"], b, D, solver=0, preconditioner=precond,
+                                  r_tolerance=1e-12, max_iter=100)
+    assert term == 0
+    assert np.allclose(x, expect, rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("pid", [2, 4, 5, 6])
+def test_dense_schur_vs_dense_qr(oracle, pid):
+    """schur_complement_solver_test.cc:127-131: |x - x_qr| / n < 1e-10 with the regulariser on."""
+    fx = FIXTURES[pid]
+    A = dense(fx)
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float)
+    expect = np.linalg.lstsq(np.vstack([A, np.diag(D)]), np.concatenate([b, np.zeros(A.shape[1])]), rcond=None)[0]
+    M = make(oracle, fx)
+    x, _, term = M.linear_solve(fx["num_eliminate_blocks"], b, D, solver=1)
+    assert term == 0
+    assert np.linalg.norm(x - expect) / A.shape[1] < 1e-10
+
+
+def test_schur_jacobi_diagonal_matches_full(oracle):
+    """SCHUR_JACOBI asks the eliminator for diagonal cells only (schur_jacobi_preconditioner.cc:87-97):
+    they must equal the diagonal blocks of the full S."""
+    fx = FIXTURES[6]
+    M = make(oracle, fx)
+    D = np.array(fx["D"], dtype=float)
+    ne_blocks = fx["num_eliminate_blocks"]
+    lhs, _ = M.schur_eliminate(ne_blocks, None, D)
+    fsizes = fx["col_sizes"][ne_blocks:]
+    diag, _ = M.schur_eliminate(ne_blocks, None, D, diagonal_only=True, diag_len=sum(s * s for s in fsizes))
+    p = 0
+    c0 = 0
+    for s in fsizes:
+        assert np.allclose(diag[p:p + s * s].reshape(s, s), lhs[c0:c0 + s, c0:c0 + s], rtol=1e-14)
+        p += s * s
+        c0 += s
