@@ -1,0 +1,250 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/sec of the ITERATIVE_SCHUR + SCHUR_JACOBI bundle-adjustment hot path.
+
+  python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl b200|reference]
+
+A "step" is one Levenberg-Marquardt iteration (ComputeTrustRegionStep: LM diagonal, implicit-Schur PCG solve,
+model cost; candidate cost evaluation; on acceptance a Jacobian evaluation + column scaling) of the configuration
+BASELINE.json names: bundle_adjuster defaults (eta 1e-2, <=500 CG iterations, SCHUR_JACOBI, Jacobi scaling, user
+ordering, no robust loss) on a BAL problem.  K steps are timed from the problem's initial point after W warm-up
+steps on the same problem (the state is reset in between, so every timed run does identical work).
+
+  value      K / device time of the device-resident loop (inputs already in HBM)
+  e2e        the same K iterations driven through the host-buffer C ABI the Ceres adapters use
+             (state/D/residual/step copies inside the timed region)
+  roofline   dominant kernel: algorithmic bytes per launch / mean CUDA-event time per launch, vs measured HBM peak
+  cpu_baseline / --impl reference: the CPU restatement of the reference path (oracle/) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lm_iterations_per_sec"
+UNIT = "LM iterations/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_problem(workload):
+    from ceres_solver_b200 import bal as B
+    if workload == "c16":
+        path = os.path.join(ROOT, "tests", "golden", "problem-16-22106-pre.txt.bz2")
+        bal = B.normalize(B.read_bal(path))
+        desc = "BAL problem-16-22106-pre (real, Normalize()d): 16 cameras / 22106 points / 83718 observations"
+    else:
+        bal = B.synthetic(workload)
+        desc = "synthetic-regen %s: %d cameras / %d points / %d observations (seed 38401)" % (
+            workload, bal.C, bal.P, bal.N)
+    return bal, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, device=0):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, bal, desc, rank0=True):
+    """The reference's own CPU path (restated in oracle/: the real Ceres cannot be built in this image — Eigen is
+    absent) on all host threads, same problem, same options."""
+    from oracle import pyoracle as po
+    nt = po.max_threads()
+    prog = po.BaProgram(bal.C, bal.P, bal.cam_idx, bal.pt_idx, np.ascontiguousarray(bal.obs).ravel())
+    state = prog.state_from_parameters(np.ascontiguousarray(bal.cameras).ravel(), np.ascontiguousarray(bal.points).ravel())
+    o = prog.default_options()
+    o.num_threads = nt
+    o.max_num_iterations = args.steps
+    if args.warmup > 0:  # touch memory / spin up the thread pool
+        ow = prog.default_options()
+        ow.num_threads = nt
+        ow.max_num_iterations = 1
+        prog.solve(state, ow)
+    t0 = time.perf_counter()
+    _, recs, times = prog.solve(state, o)
+    dt = time.perf_counter() - t0
+    iters = max(1, len(recs) - 1)
+    return {"value": iters / dt, "seconds": dt, "iterations": iters, "cores": nt, "trace": recs, "times": times}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = args.workload or "ladybug-1723"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        bal, desc = make_problem(workload)
+        r = run_reference(args, bal, desc)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": r["iterations"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["iterations"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic" if workload != "c16" else "real BAL file shipped with the reference",
+                "config": {"workload": desc, "linear_solver": "ITERATIVE_SCHUR", "preconditioner": "SCHUR_JACOBI",
+                           "eta": 1e-2, "max_linear_solver_iterations": 500},
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                 "sample": "%d LM iterations from the initial point, %d CG iterations" % (
+                                     r["iterations"], sum(int(t["ls_iterations"]) for t in r["trace"]))},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import ceres_solver_b200 as cs
+    from ceres_solver_b200 import bal as B
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world > 1:
+        raise SystemExit("multi-GPU path is not wired into bench.py yet")
+
+    bal, desc = make_problem(workload)
+    rp = B.ReducedProgram(bal)
+    state0 = rp.state(bal)
+    stream = torch.cuda.current_stream()
+    gpu = cs.Problem(rp.C, rp.P, rp.row_cam, rp.row_pt, rp.row_obs, device=local_rank, stream=stream.cuda_stream)
+
+    def timed_solve(iters, host_boundary):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        _, recs = gpu.lm_solve(state0, gpu.lm_options(max_num_iterations=iters), host_boundary=host_boundary)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        return e0.elapsed_time(e1) / 1e3, wall, recs
+
+    # warm-up
+    if args.warmup > 0:
+        timed_solve(args.warmup, False)
+        timed_solve(min(args.warmup, 2), True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    gpu.stats_reset()
+    dev_s, wall_s, recs = timed_solve(args.steps, False)
+    launches = gpu.total_launches()
+    clocks = sampler.stop()
+    iters = max(1, len(recs) - 1)
+    # end to end through the host-buffer boundary
+    gpu.stats_reset()
+    e2e_dev_s, e2e_wall_s, recs_e2e = timed_solve(args.steps, True)
+    h2d, d2h = gpu.transfer_bytes()
+    e2e_iters = max(1, len(recs_e2e) - 1)
+    # per-kernel event timing for the roofline (same steps, instrumented)
+    gpu.stats_reset()
+    gpu.profile(True)
+    timed_solve(args.steps, False)
+    stats = gpu.stats()
+    gpu.profile(False)
+    peak, peak_src = load_peaks()
+    total_ms = sum(v["ms"] for v in stats.values())
+    dom_name, dom = max(stats.items(), key=lambda kv: kv[1]["ms"])
+    achieved = dom["bytes_per_launch"] * dom["launches"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
+    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+                   "share": round(v["ms"] / total_ms, 4) if total_ms > 0 else 0.0,
+                   "GBps": round(v["bytes_per_launch"] * v["launches"] / (v["ms"] * 1e-3) / 1e9, 1)
+                   if v["ms"] > 0 and v["bytes_per_launch"] > 0 else None}
+               for k, v in stats.items() if v["launches"] > 0}
+
+    line = {"metric": METRIC, "value": iters / dev_s, "unit": UNIT, "n_gpus": world, "steps": iters,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / iters, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic" if workload != "c16" else "real BAL file shipped with the reference",
+            "config": {"workload": desc, "linear_solver": "ITERATIVE_SCHUR", "preconditioner": "SCHUR_JACOBI",
+                       "eta": 1e-2, "max_linear_solver_iterations": 500, "jacobian_bytes": 192 * rp.N,
+                       "l2": "inputs larger than L2 (J alone is %.0f MB)" % (192 * rp.N / 1e6)
+                       if 192 * rp.N > 126e6 else "working set fits L2: roofline fraction is vs HBM peak and may exceed 1",
+                       "cg_iterations": [r["ls_iterations"] for r in recs[1:]]},
+            "e2e": {"value": e2e_iters / e2e_wall_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_iters,
+                    "d2h_bytes_per_step": d2h // e2e_iters, "device_seconds": e2e_dev_s, "wall_seconds": e2e_wall_s},
+            "gpu_launches": launches, "clocks": clocks, "wall_seconds": wall_s,
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": dom["bytes_per_launch"], "launches": dom["launches"],
+                         "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},
+            "kernels": kernels,
+            "final_cost": recs[-1]["cost"]}
+    if not args.no_cpu_baseline:
+        r = run_reference(args, bal, desc)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": "%d LM iterations from the same initial point (%d CG iterations), %.1f s" % (
+                                    r["iterations"], sum(int(t["ls_iterations"]) for t in r["trace"]), r["seconds"])}
+    print(json.dumps(line))
+    gpu.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

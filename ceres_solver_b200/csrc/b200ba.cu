@@ -1,0 +1,1169 @@
+// libb200ba.so — host side of the C ABI declared in include/b200ba.h.
+//
+// Owns the device-resident bundle adjustment problem (SURVEY Appendix B layout), launches the sm_100a
+// kernels of kernels.cuh / vector_kernels.cuh on one stream, and implements
+//   * the Evaluator-shaped entry points   (internal/ceres/evaluator.h:60-168),
+//   * the SparseMatrix-shaped entry points on the device Jacobian (internal/ceres/sparse_matrix.h:67-116),
+//   * the LinearSolver-shaped ITERATIVE_SCHUR solve (iterative_schur_complement_solver.cc:64-157) with the PCG
+//     of conjugate_gradients_solver.h:109-306 running without host synchronisation inside the iteration,
+//   * a trust-region loop (trust_region_minimizer.cc / levenberg_marquardt_strategy.cc) either through the
+//     host-buffer boundary (what the Ceres adapters do) or fully device-resident.
+// There is no CPU fallback: every entry point fails with B200_ERR_NO_DEVICE / B200_ERR_CUDA if the GPU path
+// is unavailable.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#ifdef B200_WITH_NCCL
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved with dlopen at run time (see NcclApi)
+#endif
+
+#include "../../include/b200ba.h"
+#include "kernels.cuh"
+#include "vector_kernels.cuh"
+
+using namespace b200;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define CU(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(B200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                                       __FILE__, __LINE__);                                        \
+  } while (0)
+#define OK(expr)               \
+  do {                         \
+    int rc_ = (expr);          \
+    if (rc_ != B200_OK) return rc_; \
+  } while (0)
+
+enum KernelId {
+  K_EVAL_JAC = 0,
+  K_EVAL_COST,
+  K_SQNORM,
+  K_SCALE,
+  K_JMUL,
+  K_JTMUL,
+  K_JTJ,
+  K_SCHUR_INIT,
+  K_SCHUR_MUL,
+  K_DIAG_BLOCKS,
+  K_INVERT9,
+  K_BACKSUB,
+  K_MODEL_COST,
+  K_CG_VEC,
+  K_LM_VEC,
+  K_MISC,
+  K_COUNT
+};
+const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squared_column_norm", "scale_columns",
+                                     "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
+                                     "schur_multiply", "schur_diag_blocks", "invert_9x9", "back_substitute",
+                                     "model_cost", "cg_vector", "lm_vector", "misc"};
+
+#ifdef B200_WITH_NCCL
+// NCCL is bound lazily with dlopen/dlsym, and only when world_size > 1: the library then shares whatever
+// libnccl.so.2 the process already has (e.g. the one PyTorch bundles) instead of pinning its own copy, and a
+// single-GPU process never needs NCCL at all.  B200_NCCL_LIB overrides the name.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+bool load_nccl() {
+  if (g_nccl.ok) return true;
+  const char* name = getenv("B200_NCCL_LIB");
+  void* lib = dlopen(name != nullptr ? name : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) return false;
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy && g_nccl.GetErrorString;
+  return g_nccl.ok;
+}
+#endif
+
+struct EventPair {
+  cudaEvent_t a, b;
+  int kernel;
+};
+
+}  // namespace
+
+struct b200_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int C = 0, P = 0, N = 0, num_tiles = 0;
+  int np = 0;  // 3P + 9C
+  int loss_type = 0;
+  double loss_a = 1.0;
+  int rank = 0, world = 1;
+#ifdef B200_WITH_NCCL
+  ncclComm_t comm = nullptr;
+#endif
+  ProblemView view{};
+  // structure
+  TileDesc* d_tiles = nullptr;
+  int *d_cam_idx = nullptr, *d_pt_ptr = nullptr, *d_pt_of_row = nullptr;
+  double* d_obs = nullptr;
+  double* d_values = nullptr;
+  // evaluator state
+  double *d_state = nullptr, *d_residuals = nullptr, *d_gradient = nullptr, *d_tile_partial = nullptr;
+  int* d_fail = nullptr;
+  double* d_scalars = nullptr;  // small device scalar block
+  double* d_partial = nullptr;  // two-stage reduction partials
+  // generic parameter-sized / residual-sized scratch
+  double *d_vp0 = nullptr, *d_vp1 = nullptr, *d_vr0 = nullptr;
+  // linear solver state
+  double *d_b = nullptr, *d_D = nullptr, *d_ete_inv = nullptr, *d_rhs = nullptr, *d_ye = nullptr;
+  double *d_upper45 = nullptr, *d_minv = nullptr, *d_blocks = nullptr;
+  double *d_xr = nullptr, *d_p = nullptr, *d_r = nullptr, *d_z = nullptr, *d_tmp = nullptr, *d_sol = nullptr;
+  CgState* d_cg = nullptr;
+  bool schur_ready = false;
+  const double* cur_b = nullptr;  // device pointers of the current ISC Init
+  const double* cur_D = nullptr;
+  // LM state
+  double *d_scale = nullptr, *d_sqnorm = nullptr, *d_diagonal = nullptr, *d_lmD = nullptr, *d_step = nullptr,
+         *d_cand = nullptr, *d_y = nullptr;
+  // pinned host staging for scalars
+  double* h_scalars = nullptr;
+  CgState* h_cg = nullptr;
+  int* h_fail = nullptr;
+  // launch geometry
+  int grid_tile[K_COUNT];
+  // stats
+  int64_t launches[K_COUNT];
+  double ms[K_COUNT];
+  double bytes_per_launch[K_COUNT];
+  int64_t h2d_bytes = 0, d2h_bytes = 0;
+  bool profiling = false;
+  std::vector<EventPair> pending;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(T** p, size_t n) {
+  if (n == 0) n = 1;
+  CU(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return B200_OK;
+}
+
+int h2d(b200_handle* h, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  h->h2d_bytes += static_cast<int64_t>(bytes);
+  return B200_OK;
+}
+int d2h(b200_handle* h, void* dst, const void* src, size_t bytes) {
+  CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->d2h_bytes += static_cast<int64_t>(bytes);
+  return B200_OK;
+}
+
+int resolve_events(b200_handle* h) {
+  if (h->pending.empty()) return B200_OK;
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& ep : h->pending) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, ep.a, ep.b));
+    h->ms[ep.kernel] += t;
+    h->event_pool.push_back(ep.a);
+    h->event_pool.push_back(ep.b);
+  }
+  h->pending.clear();
+  return B200_OK;
+}
+
+int get_event(b200_handle* h, cudaEvent_t* e) {
+  if (!h->event_pool.empty()) {
+    *e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return B200_OK;
+  }
+  CU(cudaEventCreate(e));
+  return B200_OK;
+}
+
+// Launch wrapper: counts the launch, optionally brackets it with CUDA events, checks the launch error.
+template <typename F>
+int launch(b200_handle* h, int kid, F&& f) {
+  EventPair ep{};
+  if (h->profiling) {
+    if (h->pending.size() >= 8192) OK(resolve_events(h));
+    OK(get_event(h, &ep.a));
+    OK(get_event(h, &ep.b));
+    ep.kernel = kid;
+    CU(cudaEventRecord(ep.a, h->stream));
+  }
+  f();
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "launch of %s failed: %s", kKernelNames[kid], cudaGetErrorString(e));
+  h->launches[kid]++;
+  if (h->profiling) {
+    CU(cudaEventRecord(ep.b, h->stream));
+    h->pending.push_back(ep);
+  }
+  return B200_OK;
+}
+
+int flat_grid(const b200_handle* h, size_t n, int block) {
+  const size_t want = (n + block - 1) / block;
+  const size_t cap = static_cast<size_t>(h->sm_count) * 8;
+  return static_cast<int>(std::max<size_t>(1, std::min(want, cap)));
+}
+
+int allreduce_sum(b200_handle* h, double* buf, size_t n) {
+#ifdef B200_WITH_NCCL
+  if (h->world > 1) {
+    ncclResult_t r = g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+  }
+#else
+  (void)h; (void)buf; (void)n;
+#endif
+  return B200_OK;
+}
+
+template <typename K>
+int tile_grid(b200_handle* h, K kernel, size_t smem) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTile, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return std::max(1, std::min(h->num_tiles, h->sm_count * per_sm));
+}
+
+// ------------------------------------------------------------------------------------------------ device-pointer cores
+int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, double* d_gradient, bool want_jacobian,
+                 const double* d_scale, double* cost_out) {
+  EvalArgs a{};
+  a.state = d_state;
+  a.residuals = d_residuals;
+  a.gradient = d_gradient;
+  a.cost_partial = h->d_tile_partial;
+  a.scale = d_scale;
+  a.fail_flag = h->d_fail;
+  a.loss_type = h->loss_type;
+  a.loss_a = h->loss_a;
+  CU(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
+  const bool with_j = want_jacobian || d_gradient != nullptr;
+  if (d_gradient != nullptr)
+    CU(cudaMemsetAsync(d_gradient + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
+  const size_t smem = tile_smem_bytes<3, 1>();
+  if (with_j) {
+    OK(launch(h, K_EVAL_JAC, [&] { evaluate_kernel<true><<<h->grid_tile[K_EVAL_JAC], kTile, smem, h->stream>>>(h->view, a); }));
+  } else {
+    OK(launch(h, K_EVAL_COST, [&] { evaluate_kernel<false><<<h->grid_tile[K_EVAL_COST], kTile, smem, h->stream>>>(h->view, a); }));
+  }
+  OK(launch(h, K_MISC, [&] { sum_kernel<<<1, kVecThreads, 0, h->stream>>>(h->num_tiles, h->d_tile_partial, h->d_scalars); }));
+  if (d_gradient != nullptr) OK(allreduce_sum(h, d_gradient + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
+  OK(allreduce_sum(h, h->d_scalars, 1));
+  CU(cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->h_fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *cost_out = h->h_scalars[0];
+  if (*h->h_fail != 0 || !std::isfinite(*cost_out))
+    return fail(B200_ERR_EVALUATION_FAILED, "non-finite residual, Jacobian or cost");
+  return B200_OK;
+}
+
+int sqnorm_dev(b200_handle* h, double* d_out) {
+  CU(cudaMemsetAsync(d_out + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
+  OK(launch(h, K_SQNORM, [&] {
+    sqnorm_kernel<<<h->grid_tile[K_SQNORM], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, d_out);
+  }));
+  return allreduce_sum(h, d_out + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C));
+}
+
+int scale_dev(b200_handle* h, const double* d_scale) {
+  return launch(h, K_SCALE, [&] {
+    scale_kernel<<<flat_grid(h, 12 * static_cast<size_t>(h->N), 256), 256, 0, h->stream>>>(h->view, d_scale);
+  });
+}
+
+// ImplicitSchurComplement::Init on device pointers b [2N], D [3P+9C] or null.
+int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
+  SchurState st{};
+  st.b = d_b;
+  st.D = d_D;
+  st.ete_inv = h->d_ete_inv;
+  st.rhs = h->d_rhs;
+  st.ye = h->d_ye;
+  CU(cudaMemsetAsync(h->d_rhs, 0, sizeof(double) * 9 * h->C, h->stream));
+  OK(launch(h, K_SCHUR_INIT, [&] {
+    schur_init_kernel<<<h->grid_tile[K_SCHUR_INIT], kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view, st);
+  }));
+  OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
+  h->cur_b = d_b;
+  h->cur_D = d_D;
+  h->schur_ready = true;
+  return B200_OK;
+}
+
+// y = S x on device vectors [9C]; y is overwritten.  `done` (device int*) lets CG kernels turn the launch into a no-op.
+int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, bool seed_done_by_caller) {
+  const double* Df = h->cur_D != nullptr ? h->cur_D + 3 * static_cast<size_t>(h->P) : nullptr;
+  if (!seed_done_by_caller) {
+    const bool seed = (h->rank == 0);
+    OK(launch(h, K_MISC, [&] {
+      diag_sq_mul_kernel<<<flat_grid(h, 9 * static_cast<size_t>(h->C), 256), 256, 0, h->stream>>>(9 * h->C, seed ? Df : nullptr, d_x, d_y);
+    }));
+  }
+  OK(launch(h, K_SCHUR_MUL, [&] {
+    schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, d_x, d_y, nullptr);
+  }));
+  return allreduce_sum(h, d_y, 9 * static_cast<size_t>(h->C));
+}
+
+int precond_update_dev(b200_handle* h, int type) {
+  if (type == B200_PRECOND_IDENTITY) return B200_OK;
+  const double* Df = h->cur_D != nullptr ? h->cur_D + 3 * static_cast<size_t>(h->P) : nullptr;
+  CU(cudaMemsetAsync(h->d_upper45, 0, sizeof(double) * 45 * h->C, h->stream));
+  if (type == B200_PRECOND_SCHUR_JACOBI) {
+    OK(launch(h, K_DIAG_BLOCKS, [&] {
+      diag_blocks_kernel<true><<<h->grid_tile[K_DIAG_BLOCKS], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->d_upper45);
+    }));
+  } else {
+    OK(launch(h, K_DIAG_BLOCKS, [&] {
+      diag_blocks_kernel<false><<<h->grid_tile[K_DIAG_BLOCKS], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->d_upper45);
+    }));
+  }
+  OK(allreduce_sum(h, h->d_upper45, 45 * static_cast<size_t>(h->C)));
+  return launch(h, K_INVERT9, [&] {
+    invert9_kernel<<<(h->C + 63) / 64, 64, 0, h->stream>>>(h->C, h->d_upper45, Df, h->d_blocks, h->d_minv);
+  });
+}
+
+// IterativeSchurComplementSolver::SolveImpl on device pointers.  d_x: [3P+9C] output.
+int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const b200_solver_options* o, double* d_x,
+                    b200_solver_summary* summary) {
+  OK(schur_init_dev(h, d_b, d_D));
+  OK(precond_update_dev(h, o->preconditioner_type));
+  const int n = 9 * h->C;
+  CgParams prm{};
+  prm.n = n;
+  prm.min_iterations = o->min_num_iterations;
+  prm.max_iterations = o->max_num_iterations;
+  prm.q_tolerance = o->q_tolerance;
+  prm.r_tolerance = o->r_tolerance;
+  const double* Df = d_D != nullptr ? d_D + 3 * static_cast<size_t>(h->P) : nullptr;
+  const int precond = o->preconditioner_type == B200_PRECOND_IDENTITY ? 0 : 1;
+  const int seed = (h->rank == 0) ? 1 : 0;
+  OK(launch(h, K_CG_VEC, [&] { cg_begin_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, h->d_rhs, h->d_sol, h->d_r, h->d_cg); }));
+  const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
+  // Termination is decided on the device; the host only polls the state every few iterations
+  // (kernels become no-ops once done is set), so there is no per-iteration synchronisation.
+  int check_every = 2;
+  bool done = false;
+  int it = 0;
+  const int max_it = std::max(o->max_num_iterations, 1);
+  while (!done) {
+    for (int k = 0; k < check_every && it < max_it; ++k) {
+      ++it;
+      OK(launch(h, K_CG_VEC, [&] {
+        cg_pre_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, precond, h->d_minv, Df, seed, h->d_r, h->d_z, h->d_p, h->d_z, h->d_cg);
+      }));
+      // q aliases z exactly like the reference (conjugate_gradients_solver.h:193): z is dead once p is updated.
+      OK(launch(h, K_SCHUR_MUL, [&] {
+        schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, h->d_p, h->d_z, &h->d_cg->done);
+      }));
+      OK(allreduce_sum(h, h->d_z, n));
+      if (it % reset == 0) {
+        OK(launch(h, K_CG_VEC, [&] {
+          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 1, h->d_rhs, nullptr, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
+        }));
+        OK(schur_mul_dev(h, h->d_sol, h->d_tmp, false));
+        OK(launch(h, K_CG_VEC, [&] {
+          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 2, h->d_rhs, h->d_tmp, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
+        }));
+      } else {
+        OK(launch(h, K_CG_VEC, [&] {
+          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 0, h->d_rhs, nullptr, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
+        }));
+      }
+    }
+    CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    done = h->h_cg->done != 0 || it >= max_it;
+    check_every = std::min(check_every * 2, 8);
+  }
+  summary->num_iterations = h->h_cg->iteration;
+  summary->termination_type = h->h_cg->termination;
+  summary->residual_norm = h->h_cg->norm_r;
+  if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR) {
+    OK(launch(h, K_BACKSUB, [&] {
+      backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, d_b, h->d_sol, d_x);
+    }));
+    CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return B200_OK;
+}
+
+int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out) {
+  OK(launch(h, K_LM_VEC, [&] { reduce_final_kernel<<<1, 32, 0, h->stream>>>(blocks, slots, op_mask, h->d_partial, h->d_scalars + 8); }));
+  CU(cudaMemcpyAsync(h->h_scalars + 8, h->d_scalars + 8, sizeof(double) * slots, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < slots; ++i) host_out[i] = h->h_scalars[8 + i];
+  return B200_OK;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* b200_last_error(void) { return g_error.c_str(); }
+
+int b200_nccl_unique_id(void* out128) {
+#ifdef B200_WITH_NCCL
+  if (!load_nccl()) return fail(B200_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclGetUniqueId: %s", g_nccl.GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  std::memcpy(out128, &id, 128);
+  return B200_OK;
+#else
+  (void)out128;
+  return fail(B200_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+}
+
+void b200_solver_options_default(b200_solver_options* o) {
+  o->preconditioner_type = B200_PRECOND_SCHUR_JACOBI;
+  o->min_num_iterations = 0;
+  o->max_num_iterations = 500;  // examples/bundle_adjuster.cc:122
+  o->residual_reset_period = 10;
+  o->q_tolerance = 0.0;
+  o->r_tolerance = 0.0;
+}
+
+void b200_lm_options_default(b200_lm_options* o) {
+  o->max_num_iterations = 5;
+  o->jacobi_scaling = 1;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->reserved = 0;
+  o->eta = 1e-2;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->function_tolerance = 1e-16;
+  o->gradient_tolerance = 1e-16;
+  o->parameter_tolerance = 1e-16;
+  b200_solver_options_default(&o->linear_solver);
+}
+
+int b200_create(const b200_ba_desc* desc, b200_handle** out) {
+  if (desc == nullptr || out == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  if (desc->num_cameras <= 0 || desc->num_points <= 0 || desc->num_observations <= 0)
+    return fail(B200_ERR_INVALID_ARGUMENT, "empty problem (C=%d P=%d N=%lld)", desc->num_cameras, desc->num_points,
+                static_cast<long long>(desc->num_observations));
+  if (desc->num_observations > 2000000000LL) return fail(B200_ERR_UNSUPPORTED, "more than 2e9 row blocks");
+  if (desc->cam_idx == nullptr || desc->pt_idx == nullptr || desc->obs == nullptr)
+    return fail(B200_ERR_INVALID_ARGUMENT, "null structure array");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(B200_ERR_NO_DEVICE, "no CUDA device visible: libb200ba has no CPU fallback");
+  }
+  if (desc->device < 0 || desc->device >= ndev) return fail(B200_ERR_INVALID_ARGUMENT, "device %d of %d", desc->device, ndev);
+  CU(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major < 10)
+    return fail(B200_ERR_NO_DEVICE, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+
+  const int C = desc->num_cameras, P = desc->num_points;
+  const int N = static_cast<int>(desc->num_observations);
+  // Row structure checks: the SchurEliminator precondition (rows grouped by e block).
+  std::vector<int> pt_ptr(static_cast<size_t>(P) + 1, 0);
+  for (int i = 0; i < N; ++i) {
+    const int pt = desc->pt_idx[i], cam = desc->cam_idx[i];
+    if (pt < 0 || pt >= P || cam < 0 || cam >= C) return fail(B200_ERR_INVALID_ARGUMENT, "row %d: block id out of range", i);
+    if (i > 0 && pt < desc->pt_idx[i - 1])
+      return fail(B200_ERR_INVALID_ARGUMENT, "rows are not grouped by e block at row %d (reorder_program.cc:278-359)", i);
+    pt_ptr[pt + 1]++;
+  }
+  for (int k = 0; k < P; ++k) pt_ptr[k + 1] += pt_ptr[k];
+  // Tiles: whole points, <= kTile rows and <= kTile points each.
+  std::vector<TileDesc> tiles;
+  {
+    int k = 0;
+    while (k < P) {
+      TileDesc t;
+      t.pt_begin = k;
+      t.obs_begin = pt_ptr[k];
+      int rows = 0, pts = 0;
+      while (k < P && pts < kTile - 1) {  // pt_count + 1 chunk boundaries are loaded by one thread each
+        const int deg = pt_ptr[k + 1] - pt_ptr[k];
+        if (deg > kTile) {
+          if (pts == 0)
+            return fail(B200_ERR_UNSUPPORTED, "point %d has %d observations; more than %d per point is not supported yet", k, deg, kTile);
+          break;
+        }
+        if (rows + deg > kTile) break;
+        rows += deg;
+        ++pts;
+        ++k;
+      }
+      t.obs_count = rows;
+      t.pt_count = pts;
+      tiles.push_back(t);
+    }
+  }
+
+  b200_handle* h = new b200_handle;
+  h->device = desc->device;
+  h->sm_count = prop.multiProcessorCount;
+  h->C = C;
+  h->P = P;
+  h->N = N;
+  h->np = 3 * P + 9 * C;
+  h->num_tiles = static_cast<int>(tiles.size());
+  h->loss_type = desc->loss_type;
+  h->loss_a = desc->loss_a;
+  h->rank = desc->world_size > 1 ? desc->rank : 0;
+  h->world = desc->world_size > 1 ? desc->world_size : 1;
+  std::memset(h->launches, 0, sizeof(h->launches));
+  std::memset(h->ms, 0, sizeof(h->ms));
+  std::memset(h->bytes_per_launch, 0, sizeof(h->bytes_per_launch));
+  *out = h;  // from here on the caller owns the handle even on failure (b200_destroy is safe on partial state)
+  if (desc->stream != nullptr) {
+    h->stream = static_cast<cudaStream_t>(desc->stream);
+  } else {
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  if (h->world > 1) {
+#ifdef B200_WITH_NCCL
+    if (desc->nccl_unique_id == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
+    if (!load_nccl()) return fail(B200_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    ncclUniqueId id;
+    std::memcpy(&id, desc->nccl_unique_id, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&h->comm, h->world, id, h->rank);
+    if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+#else
+    return fail(B200_ERR_UNSUPPORTED, "built without NCCL");
+#endif
+  }
+  const size_t n = static_cast<size_t>(N);
+  std::vector<int> pt_of_row(n);
+  for (size_t i = 0; i < n; ++i) pt_of_row[i] = desc->pt_idx[i];
+  OK(dev_alloc(&h->d_tiles, tiles.size()));
+  OK(dev_alloc(&h->d_cam_idx, n));
+  OK(dev_alloc(&h->d_pt_ptr, static_cast<size_t>(P) + 1));
+  OK(dev_alloc(&h->d_pt_of_row, n));
+  OK(dev_alloc(&h->d_obs, 2 * n));
+  OK(dev_alloc(&h->d_values, 24 * n));
+  OK(dev_alloc(&h->d_state, h->np));
+  OK(dev_alloc(&h->d_residuals, 2 * n));
+  OK(dev_alloc(&h->d_gradient, h->np));
+  OK(dev_alloc(&h->d_tile_partial, tiles.size()));
+  OK(dev_alloc(&h->d_fail, 4));
+  OK(dev_alloc(&h->d_scalars, 64));
+  OK(dev_alloc(&h->d_partial, kRedBlocks * 4));
+  OK(dev_alloc(&h->d_vp0, h->np));
+  OK(dev_alloc(&h->d_vp1, h->np));
+  OK(dev_alloc(&h->d_vr0, 2 * n));
+  OK(dev_alloc(&h->d_b, 2 * n));
+  OK(dev_alloc(&h->d_D, h->np));
+  OK(dev_alloc(&h->d_ete_inv, 6 * static_cast<size_t>(P)));
+  OK(dev_alloc(&h->d_rhs, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_ye, 3 * static_cast<size_t>(P)));
+  OK(dev_alloc(&h->d_upper45, 45 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_minv, 81 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_blocks, 81 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_xr, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_p, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_r, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_z, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_tmp, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_sol, 9 * static_cast<size_t>(C)));
+  OK(dev_alloc(&h->d_cg, 1));
+  OK(dev_alloc(&h->d_scale, h->np));
+  OK(dev_alloc(&h->d_sqnorm, h->np));
+  OK(dev_alloc(&h->d_diagonal, h->np));
+  OK(dev_alloc(&h->d_lmD, h->np));
+  OK(dev_alloc(&h->d_step, h->np));
+  OK(dev_alloc(&h->d_cand, h->np));
+  OK(dev_alloc(&h->d_y, h->np));
+  CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), 64 * sizeof(double)));
+  CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_cg), sizeof(CgState)));
+  CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_fail), 4 * sizeof(int)));
+  CU(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_cam_idx, desc->cam_idx, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pt_ptr, pt_ptr.data(), pt_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_pt_of_row, pt_of_row.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_obs, desc->obs, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(h->d_values, 0, 24 * n * sizeof(double), h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->view.C = C;
+  h->view.P = P;
+  h->view.N = N;
+  h->view.num_tiles = h->num_tiles;
+  h->view.tiles = h->d_tiles;
+  h->view.cam_idx = h->d_cam_idx;
+  h->view.pt_ptr = h->d_pt_ptr;
+  h->view.pt_of_row = h->d_pt_of_row;
+  h->view.obs = h->d_obs;
+  h->view.values = h->d_values;
+
+  for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
+  h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_SQNORM] = tile_grid(h, sqnorm_kernel, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_JMUL] = tile_grid(h, jmul_kernel, tile_smem_bytes<1, 1>());
+  h->grid_tile[K_JTMUL] = tile_grid(h, jtmul_kernel<false>, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_JTJ] = tile_grid(h, jtmul_kernel<true>, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_SCHUR_INIT] = tile_grid(h, schur_init_kernel, tile_smem_bytes<9, 3>());
+  h->grid_tile[K_SCHUR_MUL] = tile_grid(h, schur_mul_kernel, tile_smem_bytes<3, 3>());
+  h->grid_tile[K_DIAG_BLOCKS] = tile_grid(h, diag_blocks_kernel<true>, tile_smem_bytes<1, 1>());
+  h->grid_tile[K_BACKSUB] = tile_grid(h, backsub_kernel, tile_smem_bytes<3, 1>());
+  h->grid_tile[K_MODEL_COST] = tile_grid(h, model_cost_kernel, tile_smem_bytes<1, 1>());
+
+  // Algorithmic (compulsory) bytes per launch, SURVEY §8d with this layout: J values 192 B/row + 4 B camera
+  // index per row + 4 B chunk boundary per point, plus the vectors each kernel must read/write once.
+  const double Nn = N, Pp = P, Cc = C;
+  h->bytes_per_launch[K_JTJ] = 196 * Nn + 4 * Pp + 24.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_SCHUR_MUL] = 196 * Nn + 52 * Pp + 216 * Cc;
+  h->bytes_per_launch[K_SCHUR_INIT] = 196 * Nn + 16 * Nn + 4 * Pp + 24 * Pp + 48 * Pp + 24 * Pp + 72 * Cc;
+  h->bytes_per_launch[K_DIAG_BLOCKS] = 196 * Nn + 52 * Pp + 360 * Cc;
+  h->bytes_per_launch[K_BACKSUB] = 196 * Nn + 16 * Nn + 52 * Pp + 24 * Pp + 72 * Cc;
+  h->bytes_per_launch[K_EVAL_JAC] = 192 * Nn + 16 * Nn + 16 * Nn + 4 * Nn + 4 * Pp + 2 * 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_EVAL_COST] = 16 * Nn + 4 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_SQNORM] = 196 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_SCALE] = 2 * 192 * Nn + 8 * Nn + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_JMUL] = 196 * Nn + 32 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_JTMUL] = 196 * Nn + 16 * Nn + 4 * Pp + 16.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_launch[K_MODEL_COST] = 196 * Nn + 16 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  return B200_OK;
+}
+
+void b200_destroy(b200_handle* h) {
+  if (h == nullptr) return;
+  cudaSetDevice(h->device);
+  if (h->stream != nullptr) cudaStreamSynchronize(h->stream);
+#ifdef B200_WITH_NCCL
+  if (h->comm != nullptr && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+#endif
+  void* dev_ptrs[] = {h->d_tiles, h->d_cam_idx, h->d_pt_ptr, h->d_pt_of_row, h->d_obs, h->d_values, h->d_state,
+                      h->d_residuals, h->d_gradient, h->d_tile_partial, h->d_fail, h->d_scalars, h->d_partial,
+                      h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
+                      h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
+                      h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y};
+  for (void* p : dev_ptrs)
+    if (p != nullptr) cudaFree(p);
+  if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->h_cg) cudaFreeHost(h->h_cg);
+  if (h->h_fail) cudaFreeHost(h->h_fail);
+  for (auto& ep : h->pending) {
+    cudaEventDestroy(ep.a);
+    cudaEventDestroy(ep.b);
+  }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->own_stream && h->stream != nullptr) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int b200_num_parameters(const b200_handle* h) { return h->np; }
+int64_t b200_num_residuals(const b200_handle* h) { return 2 * static_cast<int64_t>(h->N); }
+
+int b200_synchronize(b200_handle* h) {
+  CU(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ Evaluator
+int b200_evaluate(b200_handle* h, const double* state, double* cost, double* residuals, double* gradient,
+                  int want_jacobian) {
+  if (h == nullptr || state == nullptr || cost == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_state, state, sizeof(double) * h->np));
+  OK(evaluate_dev(h, h->d_state, residuals != nullptr ? h->d_residuals : nullptr,
+                  gradient != nullptr ? h->d_gradient : nullptr, want_jacobian != 0, nullptr, cost));
+  if (residuals != nullptr) OK(d2h(h, residuals, h->d_residuals, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+  if (gradient != nullptr) OK(d2h(h, gradient, h->d_gradient, sizeof(double) * h->np));
+  return B200_OK;
+}
+
+int b200_plus(b200_handle* h, const double* x, const double* delta, double* x_plus_delta) {
+  if (h == nullptr || x == nullptr || delta == nullptr || x_plus_delta == nullptr)
+    return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  for (int i = 0; i < h->np; ++i) x_plus_delta[i] = x[i] + delta[i];  // Euclidean blocks: program.cc:114-142
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ SparseMatrix
+int b200_jacobian_squared_column_norm(b200_handle* h, double* x) {
+  if (h == nullptr || x == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(sqnorm_dev(h, h->d_vp0));
+  return d2h(h, x, h->d_vp0, sizeof(double) * h->np);
+}
+
+int b200_jacobian_scale_columns(b200_handle* h, const double* scale) {
+  if (h == nullptr || scale == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_vp0, scale, sizeof(double) * h->np));
+  OK(scale_dev(h, h->d_vp0));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+
+int b200_jacobian_right_multiply(b200_handle* h, const double* x, double* y) {
+  if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t nr = 2 * static_cast<size_t>(h->N);
+  OK(h2d(h, h->d_vp0, x, sizeof(double) * h->np));
+  OK(h2d(h, h->d_vr0, y, sizeof(double) * nr));
+  OK(launch(h, K_JMUL, [&] {
+    jmul_kernel<<<h->grid_tile[K_JMUL], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_vp0, h->d_vr0);
+  }));
+  return d2h(h, y, h->d_vr0, sizeof(double) * nr);
+}
+
+int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y) {
+  if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t nr = 2 * static_cast<size_t>(h->N);
+  OK(h2d(h, h->d_vr0, x, sizeof(double) * nr));
+  // camera part accumulates across ranks: only rank 0 carries the incoming y there
+  OK(h2d(h, h->d_vp0, y, sizeof(double) * h->np));
+  if (h->rank != 0) CU(cudaMemsetAsync(h->d_vp0 + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
+  OK(launch(h, K_JTMUL, [&] {
+    jtmul_kernel<false><<<h->grid_tile[K_JTMUL], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_vr0, nullptr, h->d_vp0);
+  }));
+  OK(allreduce_sum(h, h->d_vp0 + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
+  return d2h(h, y, h->d_vp0, sizeof(double) * h->np);
+}
+
+int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* y) {
+  if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_vp0, x, sizeof(double) * h->np));
+  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  const double* dD = D != nullptr ? h->d_D : nullptr;
+  const size_t off = 3 * static_cast<size_t>(h->P);
+  OK(launch(h, K_MISC, [&] {
+    diag_sq_mul_kernel<<<flat_grid(h, 9 * static_cast<size_t>(h->C), 256), 256, 0, h->stream>>>(
+        9 * h->C, (dD != nullptr && h->rank == 0) ? dD + off : nullptr, h->d_vp0 + off, h->d_vp1 + off);
+  }));
+  OK(launch(h, K_JTJ, [&] {
+    jtmul_kernel<true><<<h->grid_tile[K_JTJ], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_vp0, dD, h->d_vp1);
+  }));
+  OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
+  return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
+}
+
+int b200_jacobian_get_values(b200_handle* h, double* values) {
+  if (h == nullptr || values == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  return d2h(h, values, h->d_values, sizeof(double) * 24 * static_cast<size_t>(h->N));
+}
+int b200_jacobian_set_values(b200_handle* h, const double* values) {
+  if (h == nullptr || values == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_values, values, sizeof(double) * 24 * static_cast<size_t>(h->N)));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LinearSolver
+int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b200_solver_options* opts, double* x,
+                     b200_solver_summary* summary) {
+  if (h == nullptr || b == nullptr || opts == nullptr || x == nullptr || summary == nullptr)
+    return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  OK(schur_solve_dev(h, h->d_b, D != nullptr ? h->d_D : nullptr, opts, h->d_y, summary));
+  if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR)
+    OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
+  return B200_OK;
+}
+
+int b200_schur_init(b200_handle* h, const double* b, const double* D) {
+  if (h == nullptr || b == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  OK(schur_init_dev(h, h->d_b, D != nullptr ? h->d_D : nullptr));
+  CU(cudaStreamSynchronize(h->stream));
+  return B200_OK;
+}
+int b200_schur_rhs(b200_handle* h, double* rhs) {
+  if (h == nullptr || rhs == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  return d2h(h, rhs, h->d_rhs, sizeof(double) * 9 * h->C);
+}
+int b200_schur_ete_inverse(b200_handle* h, double* out) {
+  if (h == nullptr || out == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  std::vector<double> packed(6 * static_cast<size_t>(h->P));
+  OK(d2h(h, packed.data(), h->d_ete_inv, sizeof(double) * packed.size()));
+  for (int k = 0; k < h->P; ++k) {
+    const double* s = &packed[6 * static_cast<size_t>(k)];
+    double* o = out + 9 * static_cast<size_t>(k);
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+    o[3] = s[1]; o[4] = s[3]; o[5] = s[4];
+    o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
+  }
+  return B200_OK;
+}
+int b200_schur_multiply(b200_handle* h, const double* x, double* y) {
+  if (h == nullptr || x == nullptr || y == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_xr, x, sizeof(double) * 9 * h->C));
+  OK(schur_mul_dev(h, h->d_xr, h->d_tmp, false));
+  return d2h(h, y, h->d_tmp, sizeof(double) * 9 * h->C);
+}
+int b200_schur_back_substitute(b200_handle* h, const double* z, double* y) {
+  if (h == nullptr || z == nullptr || y == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_xr, z, sizeof(double) * 9 * h->C));
+  OK(launch(h, K_BACKSUB, [&] {
+    backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->cur_b, h->d_xr, h->d_y);
+  }));
+  OK(d2h(h, y, h->d_y, sizeof(double) * 3 * static_cast<size_t>(h->P)));
+  std::memcpy(y + 3 * static_cast<size_t>(h->P), z, sizeof(double) * 9 * h->C);
+  return B200_OK;
+}
+int b200_schur_jacobi_update(b200_handle* h, double* blocks, double* inverse) {
+  if (h == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  CU(cudaSetDevice(h->device));
+  OK(precond_update_dev(h, B200_PRECOND_SCHUR_JACOBI));
+  if (blocks != nullptr) OK(d2h(h, blocks, h->d_blocks, sizeof(double) * 81 * static_cast<size_t>(h->C)));
+  if (inverse != nullptr) OK(d2h(h, inverse, h->d_minv, sizeof(double) * 81 * static_cast<size_t>(h->C)));
+  return B200_OK;
+}
+int b200_block_jacobi_update(b200_handle* h, double* inverse) {
+  if (h == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
+  CU(cudaSetDevice(h->device));
+  OK(precond_update_dev(h, B200_PRECOND_JACOBI));
+  if (inverse != nullptr) OK(d2h(h, inverse, h->d_minv, sizeof(double) * 81 * static_cast<size_t>(h->C)));
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ trust region loop
+// One implementation of TrustRegionMinimizer::Minimize's control flow; `host_boundary` selects whether the vectors
+// cross the bus through the public entry points (adapter behaviour) or stay in HBM.
+int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inout, b200_lm_iteration* trace,
+                  int max_records, int* num_records, int host_boundary) {
+  if (h == nullptr || opt == nullptr || state_inout == nullptr || trace == nullptr || num_records == nullptr)
+    return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  CU(cudaSetDevice(h->device));
+  *num_records = 0;
+  const int np = h->np;
+  const size_t nr = 2 * static_cast<size_t>(h->N);
+  const size_t off = 3 * static_cast<size_t>(h->P);
+  // host mirrors (host_boundary only)
+  std::vector<double> x, cand, residuals, gradient, step, delta, scaling, diagonal, lmD, model_res, sol, best;
+  if (host_boundary) {
+    x.assign(state_inout, state_inout + np);
+    cand.resize(np); residuals.resize(nr); gradient.resize(np); step.resize(np); delta.resize(np);
+    scaling.assign(np, 1.0); diagonal.resize(np); lmD.resize(np); model_res.resize(nr); sol.resize(np);
+    best = x;
+  } else {
+    OK(h2d(h, h->d_state, state_inout, sizeof(double) * np));
+    OK(launch(h, K_LM_VEC, [&] { fill_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, h->d_scale, 1.0); }));
+    CU(cudaMemcpyAsync(h->d_vp1, h->d_state, sizeof(double) * np, cudaMemcpyDeviceToDevice, h->stream));  // best
+  }
+  double x_cost = std::numeric_limits<double>::max(), candidate_cost = 0.0, model_cost_change = 0.0;
+  double minimum_cost = x_cost;
+  double radius = opt->initial_trust_region_radius, decrease_factor = 2.0;
+  bool reuse_diagonal = false;
+  double se_minimum = 0, se_current = 0, se_reference = 0, se_candidate = 0, se_acc_ref = 0, se_acc_cand = 0;
+  b200_lm_iteration it{};
+  int iteration = 0;
+  bool have_scaling = false;
+  const int vgrid = std::min(kRedBlocks, flat_grid(h, np, 256));
+
+  auto evaluate_gradient_and_jacobian = [&]() -> int {
+    if (host_boundary) {
+      OK(b200_evaluate(h, x.data(), &x_cost, residuals.data(), gradient.data(), 1));
+      it.cost = x_cost;
+      if (opt->jacobi_scaling) {
+        if (iteration == 0) {
+          OK(b200_jacobian_squared_column_norm(h, scaling.data()));
+          for (int i = 0; i < np; ++i) scaling[i] = 1.0 / (1.0 + std::sqrt(scaling[i]));
+        }
+        OK(b200_jacobian_scale_columns(h, scaling.data()));
+      }
+      double mx = 0, sq = 0;
+      for (int i = 0; i < np; ++i) {
+        mx = std::max(mx, std::fabs(gradient[i]));
+        sq += gradient[i] * gradient[i];
+      }
+      it.gradient_max_norm = mx;
+      it.gradient_norm = std::sqrt(sq);
+      return B200_OK;
+    }
+    // device-resident: scaling is fused into the Jacobian write once it is known
+    const bool fuse = opt->jacobi_scaling && have_scaling;
+    OK(evaluate_dev(h, h->d_state, h->d_residuals, h->d_gradient, true, fuse ? h->d_scale : nullptr, &x_cost));
+    it.cost = x_cost;
+    if (opt->jacobi_scaling && !have_scaling) {
+      OK(sqnorm_dev(h, h->d_sqnorm));
+      OK(launch(h, K_LM_VEC, [&] { jacobi_scale_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, h->d_sqnorm, h->d_scale); }));
+      OK(scale_dev(h, h->d_scale));
+      have_scaling = true;
+    }
+    OK(launch(h, K_LM_VEC, [&] { grad_norm_kernel<<<vgrid, 256, 0, h->stream>>>(np, h->d_gradient, h->d_partial); }));
+    double gn[2];
+    OK(reduce_partials(h, vgrid, 2, 0x1u, gn));
+    if (h->world > 1) {
+      // point part is sharded: combine across ranks (max / sum of squares) with the camera part counted once
+      // (handled by the caller-side reduction in the multi-GPU driver; single-rank path needs nothing).
+    }
+    it.gradient_max_norm = gn[0];
+    it.gradient_norm = std::sqrt(gn[1]);
+    return B200_OK;
+  };
+
+  it.iteration = 0;
+  OK(evaluate_gradient_and_jacobian());
+  it.step_is_valid = 1;
+  it.step_is_successful = 1;
+  se_minimum = se_current = se_reference = se_candidate = x_cost;
+  int num_consecutive_invalid = 0;
+  bool at_least_one_successful = false;
+
+  for (;;) {
+    if (it.step_is_successful && x_cost < minimum_cost) {
+      minimum_cost = x_cost;
+      if (host_boundary) best = x;
+      else CU(cudaMemcpyAsync(h->d_vp1, h->d_state, sizeof(double) * np, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    it.trust_region_radius = radius;
+    if (*num_records < max_records) trace[(*num_records)++] = it;
+    if (it.iteration >= opt->max_num_iterations) break;
+    if (it.step_is_successful && it.gradient_max_norm <= opt->gradient_tolerance) break;
+    if (it.trust_region_radius <= opt->min_trust_region_radius) break;
+
+    const double prev_gn = it.gradient_norm, prev_gmax = it.gradient_max_norm;
+    const int prev_iteration = it.iteration;
+    it = b200_lm_iteration{};
+    it.iteration = prev_iteration + 1;
+    iteration = it.iteration;
+
+    // ---- LevenbergMarquardtStrategy::ComputeStep
+    b200_solver_options so = opt->linear_solver;
+    so.q_tolerance = opt->eta;
+    so.r_tolerance = -1.0;
+    b200_solver_summary ls{};
+    bool step_finite = true;
+    if (host_boundary) {
+      if (!reuse_diagonal) {
+        OK(b200_jacobian_squared_column_norm(h, diagonal.data()));
+        for (int i = 0; i < np; ++i) diagonal[i] = std::min(std::max(diagonal[i], opt->min_lm_diagonal), opt->max_lm_diagonal);
+      }
+      for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
+      for (int i = 0; i < np; ++i) sol[i] = std::numeric_limits<double>::quiet_NaN();
+      OK(b200_schur_solve(h, residuals.data(), lmD.data(), &so, sol.data(), &ls));
+      if (ls.termination_type != B200_LS_FAILURE && ls.termination_type != B200_LS_FATAL_ERROR) {
+        for (int i = 0; i < np; ++i) step_finite = step_finite && std::isfinite(sol[i]);
+        if (step_finite)
+          for (int i = 0; i < np; ++i) step[i] = -sol[i];
+      }
+    } else {
+      if (!reuse_diagonal) OK(sqnorm_dev(h, h->d_sqnorm));
+      OK(launch(h, K_LM_VEC, [&] {
+        lm_diagonal_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, reuse_diagonal ? 0 : 1, h->d_sqnorm, h->d_diagonal, h->d_lmD,
+                                                                          opt->min_lm_diagonal, opt->max_lm_diagonal, radius);
+      }));
+      OK(schur_solve_dev(h, h->d_residuals, h->d_lmD, &so, h->d_y, &ls));
+    }
+    reuse_diagonal = true;
+    it.linear_solver_iterations = ls.num_iterations;
+    if (ls.termination_type == B200_LS_FATAL_ERROR) return fail(B200_ERR_CUDA, "linear solver fatal error");
+    bool solver_ok = ls.termination_type != B200_LS_FAILURE && step_finite;
+
+    double step_sq = 0.0, x_sq = 0.0;
+    if (solver_ok) {
+      if (host_boundary) {
+        std::fill(model_res.begin(), model_res.end(), 0.0);
+        OK(b200_jacobian_right_multiply(h, step.data(), model_res.data()));
+        double dot = 0.0;
+        for (size_t i = 0; i < nr; ++i) dot += model_res[i] * (residuals[i] + model_res[i] / 2.0);
+        model_cost_change = -dot;
+      } else {
+        // step = -y, delta = step * scaling, candidate = x + delta and the norms, in one pass
+        OK(launch(h, K_LM_VEC, [&] {
+          lm_step_kernel<<<vgrid, 256, 0, h->stream>>>(np, h->d_y, h->d_scale, h->d_state, h->d_step, h->d_cand, h->d_partial);
+        }));
+        double red[3];
+        OK(reduce_partials(h, vgrid, 3, 0u, red));
+        step_sq = red[0];
+        x_sq = red[1];
+        if (red[2] != 0.0) solver_ok = false;
+        if (solver_ok) {
+          OK(launch(h, K_MODEL_COST, [&] {
+            model_cost_kernel<<<h->grid_tile[K_MODEL_COST], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_step, h->d_residuals, h->d_tile_partial);
+          }));
+          OK(launch(h, K_MISC, [&] { sum_kernel<<<1, kVecThreads, 0, h->stream>>>(h->num_tiles, h->d_tile_partial, h->d_scalars + 1); }));
+          OK(allreduce_sum(h, h->d_scalars + 1, 1));
+          CU(cudaMemcpyAsync(h->h_scalars + 1, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+          CU(cudaStreamSynchronize(h->stream));
+          model_cost_change = h->h_scalars[1];
+        }
+      }
+      if (solver_ok) {
+        it.model_cost_change = model_cost_change;
+        it.step_is_valid = model_cost_change > 0.0;
+      }
+    }
+    if (!it.step_is_valid) {
+      if (++num_consecutive_invalid >= opt->max_num_consecutive_invalid_steps) break;
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+      it.cost = x_cost;
+      it.cost_change = 0.0;
+      it.gradient_max_norm = prev_gmax;
+      it.gradient_norm = prev_gn;
+      it.step_norm = 0.0;
+      it.relative_decrease = 0.0;
+      continue;
+    }
+    num_consecutive_invalid = 0;
+
+    // ---- ComputeCandidatePointAndEvaluateCost
+    int rc;
+    if (host_boundary) {
+      for (int i = 0; i < np; ++i) delta[i] = step[i] * scaling[i];
+      OK(b200_plus(h, x.data(), delta.data(), cand.data()));
+      rc = b200_evaluate(h, cand.data(), &candidate_cost, nullptr, nullptr, 0);
+      for (int i = 0; i < np; ++i) {
+        x_sq += x[i] * x[i];
+        step_sq += (x[i] - cand[i]) * (x[i] - cand[i]);
+      }
+    } else {
+      rc = evaluate_dev(h, h->d_cand, nullptr, nullptr, false, nullptr, &candidate_cost);
+    }
+    if (rc == B200_ERR_EVALUATION_FAILED) candidate_cost = std::numeric_limits<double>::max();
+    else if (rc != B200_OK) return rc;
+
+    it.step_norm = std::sqrt(step_sq);
+    if (at_least_one_successful && it.step_norm <= opt->parameter_tolerance * (std::sqrt(x_sq) + opt->parameter_tolerance)) break;
+    it.cost_change = x_cost - candidate_cost;
+    if (std::fabs(it.cost_change) <= opt->function_tolerance * x_cost) break;
+
+    if (candidate_cost >= std::numeric_limits<double>::max()) {
+      it.relative_decrease = std::numeric_limits<double>::lowest();
+    } else {
+      const double rd = (se_current - candidate_cost) / model_cost_change;
+      const double hist = (se_reference - candidate_cost) / (se_acc_ref + model_cost_change);
+      it.relative_decrease = std::max(rd, hist);
+    }
+    if (it.relative_decrease > opt->min_relative_decrease) {
+      at_least_one_successful = true;
+      if (host_boundary) x = cand;
+      else std::swap(h->d_state, h->d_cand);
+      OK(evaluate_gradient_and_jacobian());
+      it.step_is_successful = 1;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * it.relative_decrease - 1.0, 3));
+      radius = std::min(opt->max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      reuse_diagonal = false;
+      se_current = candidate_cost;
+      se_acc_cand += model_cost_change;
+      se_acc_ref += model_cost_change;
+      if (se_current < se_minimum) {
+        se_minimum = se_current;
+        se_candidate = se_current;
+        se_acc_cand = 0.0;
+        se_reference = se_candidate;
+        se_acc_ref = se_acc_cand;
+      } else if (se_current > se_candidate) {
+        se_candidate = se_current;
+        se_acc_cand = 0.0;
+      }
+    } else {
+      it.step_is_successful = 0;
+      it.cost = candidate_cost;
+      it.gradient_norm = prev_gn;
+      it.gradient_max_norm = prev_gmax;
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      reuse_diagonal = true;
+    }
+  }
+  if (host_boundary) std::memcpy(state_inout, best.data(), sizeof(double) * np);
+  else OK(d2h(h, state_inout, h->d_vp1, sizeof(double) * np));
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ instrumentation
+int b200_profile_enable(b200_handle* h, int on) {
+  if (h == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+  OK(resolve_events(h));
+  h->profiling = on != 0;
+  return B200_OK;
+}
+int b200_stats_reset(b200_handle* h) {
+  if (h == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+  OK(resolve_events(h));
+  std::memset(h->launches, 0, sizeof(h->launches));
+  std::memset(h->ms, 0, sizeof(h->ms));
+  h->h2d_bytes = 0;
+  h->d2h_bytes = 0;
+  return B200_OK;
+}
+int b200_stats_get(b200_handle* h, b200_kernel_stat* out, int max_entries, int* num_entries) {
+  if (h == nullptr || out == nullptr || num_entries == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  OK(resolve_events(h));
+  int n = 0;
+  for (int k = 0; k < K_COUNT && n < max_entries; ++k) {
+    std::memset(&out[n], 0, sizeof(out[n]));
+    std::strncpy(out[n].name, kKernelNames[k], sizeof(out[n].name) - 1);
+    out[n].launches = h->launches[k];
+    out[n].device_ms = h->ms[k];
+    out[n].bytes_per_launch = h->bytes_per_launch[k];
+    ++n;
+  }
+  *num_entries = n;
+  return B200_OK;
+}
+int64_t b200_total_launches(const b200_handle* h) {
+  int64_t t = 0;
+  for (int k = 0; k < K_COUNT; ++k) t += h->launches[k];
+  return t;
+}
+int b200_transfer_bytes(const b200_handle* h, int64_t* h2d_out, int64_t* d2h_out) {
+  if (h == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+  if (h2d_out) *h2d_out = h->h2d_bytes;
+  if (d2h_out) *d2h_out = h->d2h_bytes;
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,333 @@
+"""Parity of the CUDA hot path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances: north_star asks for 1e-6 relative on residuals and step norm; the component checks below are far
+tighter (FP64 everywhere, only summation order differs), the 1e-6 bound is asserted on the LM trajectories.
+Every test here needs a B200 (`-m gpu`).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import ceres_solver_b200 as m
+    m.lib()
+    return m
+
+
+class Case:
+    """A BAL problem set up identically for the oracle and for the GPU library."""
+
+    def __init__(self, cs, oracle, bal, use_huber=False):
+        from ceres_solver_b200 import bal as B
+        self.rp = B.ReducedProgram(bal)
+        self.orc = oracle.BaProgram(bal.C, bal.P, bal.cam_idx, bal.pt_idx, np.ascontiguousarray(bal.obs).ravel(),
+                                    use_huber=use_huber, huber_a=1.0)
+        assert np.array_equal(self.rp.row_pt, self.orc.row_pt) and np.array_equal(self.rp.row_cam, self.orc.row_cam)
+        self.gpu = cs.Problem(self.rp.C, self.rp.P, self.rp.row_cam, self.rp.row_pt, self.rp.row_obs,
+                              loss_type=cs.LOSS_HUBER if use_huber else cs.LOSS_TRIVIAL, loss_a=1.0)
+        self.state = self.rp.state(bal)
+        assert np.array_equal(self.state, self.orc.state_from_parameters(np.ascontiguousarray(bal.cameras).ravel(),
+                                                                          np.ascontiguousarray(bal.points).ravel()))
+
+
+@pytest.fixture(scope="module")
+def c16_case(cs, oracle, c16):
+    from ceres_solver_b200 import bal as B
+    bal = B.Bal(c16.cam_idx, c16.pt_idx, c16.obs, c16.cameras, c16.points)
+    return Case(cs, oracle, bal)
+
+
+@pytest.fixture(scope="module")
+def tiny_case(cs, oracle):
+    from ceres_solver_b200 import bal as B
+    return Case(cs, oracle, B.synthetic("tiny"))
+
+
+def _evaluate_both(case):
+    ok, cost, res, grad = case.gpu.evaluate(case.state)
+    ok_o, cost_o, res_o, grad_o = case.orc.evaluate(case.state, nt=8)
+    assert ok and ok_o
+    return (cost, res, grad), (cost_o, res_o, grad_o)
+
+
+@pytest.mark.parametrize("which", ["c16", "tiny"])
+def test_evaluate(which, c16_case, tiny_case):
+    case = c16_case if which == "c16" else tiny_case
+    (cost, res, grad), (cost_o, res_o, grad_o) = _evaluate_both(case)
+    assert abs(cost - cost_o) <= 1e-13 * cost_o
+    assert relerr(res, res_o) < 1e-12
+    assert relerr(grad, grad_o) < 1e-11
+    v, v_o = case.gpu.jacobian_values(), case.orc.jacobian().values()
+    assert relerr(v, v_o) < 1e-12
+    assert np.abs(v - v_o).max() <= 1e-9 * np.abs(v_o).max()
+    if which == "c16":
+        assert "%.6e" % cost == "4.185660e+06"  # docs/source/installation.rst:214
+    # cost-only evaluation (candidate point): same cost, Jacobian untouched
+    ok, cost2, _, _ = case.gpu.evaluate(case.state, want_residuals=False, want_gradient=False, want_jacobian=False)
+    assert ok and abs(cost2 - cost_o) <= 1e-13 * cost_o
+    assert np.array_equal(case.gpu.jacobian_values(), v)
+
+
+def test_evaluate_huber(cs, oracle, c16):
+    from ceres_solver_b200 import bal as B
+    case = Case(cs, oracle, B.Bal(c16.cam_idx, c16.pt_idx, c16.obs, c16.cameras, c16.points), use_huber=True)
+    (cost, res, grad), (cost_o, res_o, grad_o) = _evaluate_both(case)
+    assert abs(cost - cost_o) <= 1e-13 * cost_o
+    assert relerr(res, res_o) < 1e-12
+    assert relerr(grad, grad_o) < 1e-11
+    assert relerr(case.gpu.jacobian_values(), case.orc.jacobian().values()) < 1e-12
+
+
+def test_evaluate_theta_zero_and_failure(cs, oracle):
+    """rotation.h:873 exact-zero branch; a point on the camera plane (p_z = 0) must make Evaluate fail."""
+    cams = np.array([[0, 0, 0, 0.1, -0.2, -5.0, 800.0, 1e-7, 1e-13]], dtype=float)
+    pts = np.array([[0.3, -0.4, 1.5], [1.0, 0.5, 2.0]])
+    obs = np.array([10.0, -3.0, 5.0, 8.0])
+    gpu = cs.Problem(1, 2, [0, 0], [0, 1], obs)
+    orc = oracle.BaProgram(1, 2, [0, 0], [0, 1], obs)
+    state = orc.state_from_parameters(cams.ravel(), pts.ravel())
+    ok, cost, res, grad = gpu.evaluate(state)
+    _, cost_o, res_o, grad_o = orc.evaluate(state)
+    assert ok and abs(cost - cost_o) <= 1e-14 * cost_o
+    assert relerr(gpu.jacobian_values(), orc.jacobian().values()) < 1e-13
+    assert relerr(grad, grad_o) < 1e-13
+    bad = state.copy()
+    bad[2] = 5.0  # p_z = X_z + t_z = 0 for point 0
+    ok, _, _, _ = gpu.evaluate(bad)
+    ok_o, _, _, _ = orc.evaluate(bad)
+    assert not ok and not ok_o
+
+
+def test_sparse_matrix_ops(c16_case):
+    case = c16_case
+    _evaluate_both(case)
+    J = case.orc.jacobian()
+    rng = np.random.RandomState(1)
+    x = rng.randn(case.gpu.num_parameters)
+    y = rng.randn(case.gpu.num_residuals)
+    assert relerr(case.gpu.squared_column_norm(), J.squared_column_norm()) < 1e-13
+    assert relerr(case.gpu.right_multiply(x), J.right_multiply(x)) < 1e-13
+    y0 = rng.randn(case.gpu.num_residuals)
+    assert relerr(case.gpu.right_multiply(x, y0), y0 + J.right_multiply(x)) < 1e-13
+    assert relerr(case.gpu.left_multiply(y), J.left_multiply(y)) < 1e-12
+    D = rng.rand(case.gpu.num_parameters) + 0.5
+    expect = J.left_multiply(J.right_multiply(x)) + D * D * x
+    assert relerr(case.gpu.jtj_multiply(x, D), expect) < 1e-12
+    assert relerr(case.gpu.jtj_multiply(x, None), J.left_multiply(J.right_multiply(x))) < 1e-12
+    s = 1.0 / (1.0 + np.sqrt(J.squared_column_norm()))
+    case.gpu.scale_columns(s)
+    J.scale_columns(s, nt=8)
+    assert relerr(case.gpu.jacobian_values(), J.values()) < 1e-15
+
+
+def _scaled_system(case):
+    """Jacobi-scaled J, residuals b and an LM diagonal D as the first LM iteration sees them."""
+    (cost, res, grad), _ = _evaluate_both(case)
+    J = case.orc.jacobian()
+    s = 1.0 / (1.0 + np.sqrt(J.squared_column_norm()))
+    case.gpu.scale_columns(s)
+    J.scale_columns(s, nt=8)
+    diag = np.clip(J.squared_column_norm(), 1e-6, 1e32)
+    D = np.sqrt(diag / 1e4)
+    return J, res, D
+
+
+@pytest.mark.parametrize("which", ["c16", "tiny"])
+@pytest.mark.parametrize("use_D", [True, False])
+def test_implicit_schur_pieces(which, use_D, c16_case, tiny_case, oracle):
+    case = c16_case if which == "c16" else tiny_case
+    J, b, D = _scaled_system(case)
+    if not use_D:
+        D = None
+    isc = oracle.ImplicitSchur(J, case.gpu.P, want_ftf=True, nt=8)
+    isc.init(D, b)
+    case.gpu.schur_init(b, D)
+    assert relerr(case.gpu.schur_ete_inverse(), isc.ete_inverse()) < 1e-11
+    assert relerr(case.gpu.schur_rhs(), isc.rhs()) < 1e-10
+    rng = np.random.RandomState(2)
+    for _ in range(3):
+        x = rng.randn(9 * case.gpu.C)
+        assert relerr(case.gpu.schur_multiply(x), isc.right_multiply(x)) < 1e-10
+    z = rng.randn(9 * case.gpu.C)
+    assert relerr(case.gpu.schur_back_substitute(z), isc.back_substitute(z)) < 1e-10
+    # SCHUR_JACOBI blocks = diagonal blocks of the eliminator's S (schur_jacobi_preconditioner.cc:87-97)
+    C = case.gpu.C
+    diag, _ = J.schur_eliminate(case.gpu.P, None, D, diagonal_only=True, diag_len=81 * C, nt=8, n_f=9 * C)
+    blocks, inv = case.gpu.schur_jacobi_update()
+    assert relerr(blocks, diag) < 1e-10
+    for c in range(min(C, 16)):
+        m = diag[81 * c:81 * (c + 1)].reshape(9, 9)
+        assert relerr(inv[81 * c:81 * (c + 1)].reshape(9, 9), np.linalg.inv(m)) < 1e-7
+    # JACOBI blocks: (F'F + D_f^2)^-1
+    ftf = J.block_diagonal(case.gpu.P, 1, nt=8)
+    jinv = case.gpu.block_jacobi_update()
+    for c in range(min(C, 16)):
+        m = ftf[81 * c:81 * (c + 1)].reshape(9, 9).copy()
+        if D is not None:
+            m += np.diag(D[3 * case.gpu.P + 9 * c:3 * case.gpu.P + 9 * c + 9] ** 2)
+        assert relerr(jinv[81 * c:81 * (c + 1)].reshape(9, 9), np.linalg.inv(m)) < 1e-7
+
+
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_schur_solve_matches_oracle(precond, c16_case, cs):
+    case = c16_case
+    J, b, D = _scaled_system(case)
+    x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, preconditioner=precond, q_tolerance=1e-2,
+                                        r_tolerance=-1.0, max_iter=500, nt=8)
+    o = case.gpu.solver_options(preconditioner_type=precond, q_tolerance=1e-2, r_tolerance=-1.0)
+    x, its, term = case.gpu.schur_solve(b, D, o)
+    assert term == term_o == cs.LS_SUCCESS
+    assert its == its_o
+    assert relerr(x, x_o) < 1e-8
+    # tight solve, residual-based stop, several residual resets: solution of the normal equations
+    x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, preconditioner=precond, q_tolerance=0.0,
+                                        r_tolerance=1e-10, max_iter=500, nt=8)
+    o = case.gpu.solver_options(preconditioner_type=precond, q_tolerance=0.0, r_tolerance=1e-10)
+    x, its, term = case.gpu.schur_solve(b, D, o)
+    assert term == term_o
+    assert abs(its - its_o) <= 1
+    assert relerr(x, x_o) < 1e-7
+    x_exact, _, _ = J.linear_solve(case.gpu.P, b, D, solver=1, nt=8)
+    if term == cs.LS_SUCCESS:
+        assert relerr(x, x_exact) < 1e-6
+
+
+def test_schur_solve_max_iterations(c16_case, cs):
+    case = c16_case
+    J, b, D = _scaled_system(case)
+    o = case.gpu.solver_options(q_tolerance=0.0, r_tolerance=0.0, max_num_iterations=7)
+    x, its, term = case.gpu.schur_solve(b, D, o)
+    x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, q_tolerance=0.0, r_tolerance=0.0, max_iter=7, nt=8)
+    assert (its, term) == (its_o, term_o) == (7, cs.LS_NO_CONVERGENCE)
+    assert relerr(x, x_o) < 1e-9
+
+
+def _compare_traces(recs, recs_o):
+    assert len(recs) == len(recs_o)
+    for a, b in zip(recs, recs_o):
+        assert a["iteration"] == int(b["iteration"])
+        assert a["ls_iterations"] == int(b["ls_iterations"]), (a, b)
+        assert a["step_is_successful"] == int(b["step_is_successful"])
+        assert abs(a["cost"] - b["cost"]) <= 1e-6 * abs(b["cost"]), (a, b)
+        assert abs(a["step_norm"] - b["step_norm"]) <= 1e-6 * max(abs(b["step_norm"]), 1e-30), (a, b)
+        assert abs(a["tr_radius"] - b["tr_radius"]) <= 1e-6 * b["tr_radius"]
+        assert abs(a["gradient_max_norm"] - b["gradient_max_norm"]) <= 1e-6 * max(b["gradient_max_norm"], 1e-30)
+
+
+@pytest.mark.parametrize("host_boundary", [False, True])
+def test_lm_trajectory_c16(host_boundary, c16_case):
+    """BASELINE.json configs[1]: BAL 16-22106, ITERATIVE_SCHUR + SCHUR_JACOBI, 5 iterations, eta 1e-2."""
+    case = c16_case
+    o = case.orc.default_options()
+    o.num_threads = 8
+    state_o, recs_o, _ = case.orc.solve(case.state, o)
+    state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(), host_boundary=host_boundary)
+    _compare_traces(recs, recs_o)
+    assert [r["ls_iterations"] for r in recs[1:]] == [5, 16, 23, 23, 15]
+    assert relerr(state, state_o) < 1e-6
+    # final residuals agree to 1e-6 relative
+    _, _, res, _ = case.gpu.evaluate(state, want_gradient=False, want_jacobian=False)
+    _, _, res_o, _ = case.orc.evaluate(state_o, want_gradient=False, want_jacobian=False)
+    assert relerr(res, res_o) < 1e-6
+
+
+@pytest.mark.parametrize("host_boundary", [False, True])
+def test_lm_trajectory_tiny(host_boundary, tiny_case):
+    case = tiny_case
+    o = case.orc.default_options()
+    state_o, recs_o, _ = case.orc.solve(case.state, o)
+    state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(), host_boundary=host_boundary)
+    _compare_traces(recs[:4], recs_o[:4])  # later iterations sit at the noise floor of the CG stopping rule
+
+
+def test_ragged_structure_and_duplicates(cs, oracle):
+    """Degree-1 points, a point seen twice by the same camera (chunk buffer accumulation,
+    schur_eliminator_impl.h:493-507), cameras with very different loads, tiles with many tiny points."""
+    rng = np.random.RandomState(5)
+    from ceres_solver_b200 import bal as B
+    base = B.synthetic_bal(8, 400, 1200, seed=7, max_degree=8)
+    cam = base.cam_idx.copy()
+    pt = base.pt_idx.copy()
+    obs = base.obs.copy()
+    # duplicate: point 3 observed twice by its first camera
+    j = np.flatnonzero(pt == 3)[0]
+    cam = np.insert(cam, j + 1, cam[j])
+    pt = np.insert(pt, j + 1, 3)
+    obs = np.insert(obs, j + 1, obs[j] + 0.7, axis=0)
+    # make points 10..19 degree one
+    keep = np.ones(pt.size, dtype=bool)
+    for p in range(10, 20):
+        idx = np.flatnonzero(pt == p)
+        keep[idx[1:]] = False
+    bal = B.Bal(cam[keep], pt[keep], obs[keep], base.cameras, base.points)
+    case = Case(cs, oracle, bal)
+    J, b, D = _scaled_system(case)
+    isc = oracle.ImplicitSchur(J, case.gpu.P, nt=1)
+    isc.init(D, b)
+    case.gpu.schur_init(b, D)
+    x = rng.randn(9 * case.gpu.C)
+    assert relerr(case.gpu.schur_multiply(x), isc.right_multiply(x)) < 1e-10
+    C = case.gpu.C
+    diag, _ = J.schur_eliminate(case.gpu.P, None, D, diagonal_only=True, diag_len=81 * C, n_f=9 * C)
+    blocks, _ = case.gpu.schur_jacobi_update()
+    assert relerr(blocks, diag) < 1e-10
+    x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, q_tolerance=1e-3, r_tolerance=-1.0)
+    xg, its, term = case.gpu.schur_solve(b, D, case.gpu.solver_options(q_tolerance=1e-3, r_tolerance=-1.0))
+    assert (its, term) == (its_o, term_o)
+    assert relerr(xg, x_o) < 1e-8
+
+
+def test_argument_errors(cs):
+    with pytest.raises(cs.B200Error) as e:
+        cs.Problem(2, 3, [0, 1, 0], [0, 2, 1], np.zeros(6))  # rows not grouped by e block
+    assert e.value.code == -1
+    with pytest.raises(cs.B200Error):
+        cs.Problem(2, 3, [0, 5, 0], [0, 1, 2], np.zeros(6))  # camera id out of range
+    p = cs.Problem(2, 3, [0, 1, 0], [0, 1, 2], np.zeros(6))
+    with pytest.raises(cs.B200Error):
+        p.schur_multiply(np.zeros(18))  # before schur_init
+    p.close()
+
+
+def test_full_size_properties(cs):
+    """Ladybug-1723-sized synthetic problem (BASELINE.json configs[2]); size-independent properties:
+    symmetry and positive definiteness of S, J'J x against two separate products, S x against
+    F'F x - F'E (E'E)^-1 E'F x assembled from J products with E/F-masked vectors."""
+    from ceres_solver_b200 import bal as B
+    bal = B.synthetic("ladybug-1723")
+    rp = B.ReducedProgram(bal)
+    gpu = cs.Problem(rp.C, rp.P, rp.row_cam, rp.row_pt, rp.row_obs)
+    state = rp.state(bal)
+    ok, cost, res, grad = gpu.evaluate(state)
+    assert ok and np.isfinite(cost)
+    assert abs(0.5 * res @ res - cost) <= 1e-12 * cost
+    assert relerr(gpu.left_multiply(res), grad) < 1e-11
+    rng = np.random.RandomState(3)
+    x = rng.randn(gpu.num_parameters)
+    D = rng.rand(gpu.num_parameters) + 0.5
+    assert relerr(gpu.jtj_multiply(x, D), gpu.left_multiply(gpu.right_multiply(x)) + D * D * x) < 1e-12
+    nE = 3 * gpu.P
+    gpu.schur_init(res, D)
+    u, v = rng.randn(9 * gpu.C), rng.randn(9 * gpu.C)
+    Su, Sv = gpu.schur_multiply(u), gpu.schur_multiply(v)
+    assert abs(u @ Sv - v @ Su) <= 1e-11 * abs(u @ Sv)
+    assert u @ Su > 0 and v @ Sv > 0
+    # S u from unfused pieces: y = F u; w = (E'E + De^2)^-1 E'y; S u = F'(y - E w) + Df^2 u
+    xu = np.concatenate([np.zeros(nE), u])
+    y = gpu.right_multiply(xu)
+    Ety = gpu.left_multiply(y)[:nE]
+    Pinv = gpu.schur_ete_inverse().reshape(-1, 3, 3)
+    w = np.einsum("kij,kj->ki", Pinv, Ety.reshape(-1, 3)).ravel()
+    y2 = y - gpu.right_multiply(np.concatenate([w, np.zeros(9 * gpu.C)]))
+    expect = gpu.left_multiply(y2)[nE:] + D[nE:] ** 2 * u
+    assert relerr(Su, expect) < 1e-10
+    gpu.close()

@@ -1,0 +1,127 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every declared symbol, fails
+loudly without a GPU (no CPU fallback), and the host-side problem preparation (BAL reader, Normalize, reduced
+program order, synthetic regeneration) agrees with the oracle's restatement of the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def cs():
+    import __graft_entry__ as g
+    g.build()
+    import ceres_solver_b200 as m
+    return m
+
+
+def test_library_exports_every_declared_symbol(cs):
+    header = open(os.path.join(ROOT, "include", "b200ba.h")).read()
+    declared = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200_handle"}
+    assert declared, "no declarations parsed"
+    lib = cs.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libb200ba.so does not export %s" % name
+    assert declared == set(cs.SYMBOLS), (declared ^ set(cs.SYMBOLS))
+
+
+def test_struct_layouts_match_header(cs):
+    from ceres_solver_b200 import binding as b
+    o = b.SolverOptions()
+    cs.lib().b200_solver_options_default(ctypes.byref(o))
+    assert (o.preconditioner_type, o.max_num_iterations, o.residual_reset_period) == (2, 500, 10)
+    lm = b.LmOptions()
+    cs.lib().b200_lm_options_default(ctypes.byref(lm))
+    assert lm.max_num_iterations == 5 and lm.eta == 1e-2 and lm.initial_trust_region_radius == 1e4
+    assert lm.min_lm_diagonal == 1e-6 and lm.max_lm_diagonal == 1e32 and lm.linear_solver.max_num_iterations == 500
+
+
+def test_no_gpu_means_loud_failure_not_fallback(cs):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    with pytest.raises(cs.B200Error) as e:
+        cs.Problem(2, 3, [0, 1, 0], [0, 1, 2], np.zeros(6))
+    assert e.value.code == -4  # B200_ERR_NO_DEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ceres_solver_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"import\s+oracle|from\s+oracle|oracle/|libceres_oracle|pyoracle", text), \
+                    "%s reaches into the oracle" % os.path.join(dirpath, f)
+
+
+def test_bal_reader_and_normalize(oracle, c16_raw, c16):
+    from ceres_solver_b200 import bal as B
+    b = B.read_bal(os.path.join(ROOT, "tests", "golden", "problem-16-22106-pre.txt.bz2"))
+    assert (b.C, b.P, b.N) == (16, 22106, 83718)
+    assert np.array_equal(b.cam_idx, c16_raw.cam_idx) and np.array_equal(b.pt_idx, c16_raw.pt_idx)
+    assert np.array_equal(b.obs.ravel(), c16_raw.obs)
+    assert np.array_equal(b.cameras.ravel(), c16_raw.cameras) and np.array_equal(b.points.ravel(), c16_raw.points)
+    n = B.normalize(b)
+    assert np.allclose(n.points.ravel(), c16.points, rtol=1e-14, atol=1e-12)
+    assert np.allclose(n.cameras.ravel(), c16.cameras, rtol=1e-13, atol=1e-12)
+
+
+def test_reduced_program_order(oracle, c16):
+    from ceres_solver_b200 import bal as B
+    b = B.Bal(c16.cam_idx, c16.pt_idx, c16.obs, c16.cameras, c16.points)
+    rp = B.ReducedProgram(b)
+    op = oracle.BaProgram(c16.C, c16.P, c16.cam_idx, c16.pt_idx, c16.obs)
+    for k in ("point_of_eblock", "camera_of_fblock", "obs_of_row", "row_pt", "row_cam"):
+        assert np.array_equal(getattr(rp, k), getattr(op, k)), k
+    assert np.array_equal(rp.row_obs.ravel(), op.row_obs)
+    assert np.array_equal(rp.state(b), op.state_from_parameters(c16.cameras, c16.points))
+    # unordered input (shuffled observations): still the reference's rule
+    rng = np.random.RandomState(0)
+    perm = rng.permutation(b.N)[:5000]
+    sb = B.Bal(b.cam_idx[perm], b.pt_idx[perm], b.obs[perm], b.cameras, b.points)
+    rp = B.ReducedProgram(sb)
+    op = oracle.BaProgram(sb.C, sb.P, sb.cam_idx, sb.pt_idx, sb.obs.ravel())
+    for k in ("point_of_eblock", "camera_of_fblock", "obs_of_row", "row_pt", "row_cam"):
+        assert np.array_equal(getattr(rp, k), getattr(op, k)), k
+
+
+def test_synthetic_is_seeded_and_well_formed():
+    from ceres_solver_b200 import bal as B
+    a = B.synthetic("tiny")
+    b = B.synthetic("tiny")
+    assert np.array_equal(a.obs, b.obs) and np.array_equal(a.cam_idx, b.cam_idx)
+    C, P, N = B.SHAPES["tiny"]
+    assert (a.C, a.P, a.N) == (C, P, N)
+    deg = np.bincount(a.pt_idx, minlength=P)
+    assert deg.min() >= 2
+    key = a.pt_idx.astype(np.int64) * C + a.cam_idx
+    assert np.unique(key).size == N  # a camera sees a point at most once
+    assert np.all(np.diff(a.pt_idx) >= 0)
+    # every point is in front of its cameras (Snavely convention: p_z < 0)
+    cam = a.cameras[a.cam_idx]
+    p = B.angle_axis_rotate(cam[:, 0:3], a.points[a.pt_idx]) + cam[:, 3:6]
+    assert np.all(p[:, 2] < 0)
+    proj = B.snavely_project(a.cameras, a.points, a.cam_idx, a.pt_idx)
+    assert np.abs(proj - a.obs).max() < 200.0
+
+
+def test_shard_partition_covers_all_rows():
+    from ceres_solver_b200 import bal as B
+    rp = B.ReducedProgram(B.synthetic("tiny"))
+    for world in (1, 2, 3, 8):
+        rows = 0
+        prev_hi = 0
+        for r in range(world):
+            lo, hi, rlo, rhi = rp.shard(r, world)
+            assert lo == prev_hi
+            prev_hi = hi
+            assert np.all(rp.row_pt[rlo:rhi] >= lo) and np.all(rp.row_pt[rlo:rhi] < hi)
+            rows += rhi - rlo
+        assert prev_hi == rp.P and rows == rp.N
