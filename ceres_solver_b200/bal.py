@@ -210,9 +210,133 @@ def synthetic_bal(num_cameras, num_points, num_observations, seed=38401, max_deg
     return Bal(cam_idx.astype(np.int32), pt_idx.astype(np.int32), obs, cams0, pts0)
 
 
+def _look_at_cameras(centers, targets, rng):
+    """Cameras at `centers` looking at `targets` (Snavely convention: the camera looks down its -z axis), with
+    f~U(500,1500), l1~N(0,1e-7), l2~N(0,1e-13)."""
+    from scipy.spatial.transform import Rotation
+    C = centers.shape[0]
+    z = centers - targets
+    z /= np.linalg.norm(z, axis=1, keepdims=True)
+    up = np.tile(np.array([0.0, 0.0, 1.0]), (C, 1))
+    x = np.cross(up, z)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    y = np.cross(z, x)
+    R = np.stack([x, y, z], axis=1)
+    cams = np.zeros((C, 9))
+    cams[:, 0:3] = Rotation.from_matrix(R).as_rotvec()
+    cams[:, 3:6] = -np.einsum("cij,cj->ci", R, centers)
+    cams[:, 6] = rng.uniform(500.0, 1500.0, C)
+    cams[:, 7] = rng.normal(0.0, 1e-7, C)
+    cams[:, 8] = rng.normal(0.0, 1e-13, C)
+    return cams
+
+
+def _degrees(rng, P, N, max_degree):
+    """Per-point track lengths: 2 + geometric tail, fixed up to sum exactly to N."""
+    if not (2 * P <= N <= max_degree * P):
+        raise ValueError("need 2P <= N <= max_degree*P")
+    extra = N - 2 * P
+    deg = 2 + np.minimum(rng.geometric(1.0 / (1.0 + extra / P), P) - 1, max_degree - 2)
+    diff = N - int(deg.sum())
+    while diff != 0:
+        cand = np.flatnonzero(deg < max_degree) if diff > 0 else np.flatnonzero(deg > 2)
+        pick = np.unique(cand[rng.randint(0, cand.size, min(abs(diff), cand.size))])
+        deg[pick] += 1 if diff > 0 else -1
+        diff = N - int(deg.sum())
+    return deg
+
+
+def _finish(rng, cams, pts, cam_idx, pt_idx):
+    """Noisy observations of the true geometry + the perturbed initial guess (SURVEY §8d sigmas)."""
+    N = cam_idx.shape[0]
+    obs = snavely_project(cams, pts, cam_idx, pt_idx) + rng.normal(0.0, 0.5, (N, 2))
+    C, P = cams.shape[0], pts.shape[0]
+    cams0 = cams.copy()
+    center = -angle_axis_rotate(-cams[:, 0:3], cams[:, 3:6])
+    w0 = cams[:, 0:3] + rng.normal(0.0, 1e-3, (C, 3))
+    cams0[:, 0:3] = w0
+    cams0[:, 3:6] = -angle_axis_rotate(w0, center) + rng.normal(0.0, 1e-1, (C, 3))
+    pts0 = pts + rng.normal(0.0, 1e-1, (P, 3))
+    return Bal(cam_idx.astype(np.int32), pt_idx.astype(np.int32), obs, cams0, pts0)
+
+
+def synthetic_sequence(num_cameras, num_points, num_observations, seed=38401, max_degree=48):
+    """Ladybug-like capture: the cameras are consecutive frames of a vehicle driving a loop (radius 300, looking
+    outward and slightly ahead); every point is a track over `degree` CONSECUTIVE frames, created in frame order —
+    the structure an incremental reconstruction of a video produces, and the one BAL's Ladybug sets have."""
+    rng = np.random.RandomState(seed)
+    C, P, N = int(num_cameras), int(num_points), int(num_observations)
+    max_degree = min(max_degree, C)
+    phi = 2.0 * np.pi * np.arange(C) / C
+    radial = np.stack([np.cos(phi), np.sin(phi), np.zeros(C)], axis=1)
+    tangent = np.stack([-np.sin(phi), np.cos(phi), np.zeros(C)], axis=1)
+    centers = 300.0 * radial + np.stack([np.zeros(C), np.zeros(C), 1.5 * np.sin(7 * phi)], axis=1)
+    cams = _look_at_cameras(centers, centers + 10.0 * radial + 3.0 * tangent, rng)
+    deg = _degrees(rng, P, N, max_degree)
+    first = np.minimum(rng.randint(0, C, P), C - deg)            # no wrap-around at the end of the sequence
+    order = np.argsort(first, kind="stable")                     # points are created in frame order
+    first, deg = first[order], deg[order]
+    mid = first + deg // 2
+    depth = rng.uniform(12.0, 40.0, P)
+    pts = centers[mid] + depth[:, None] * radial[mid] + (0.2 * depth * rng.normal(0.0, 1.0, P))[:, None] * tangent[mid]
+    pts[:, 2] += 0.2 * depth * rng.normal(0.0, 1.0, P)
+    pt_idx = np.repeat(np.arange(P, dtype=np.int64), deg)
+    ptr = np.concatenate([[0], np.cumsum(deg)])
+    within = np.arange(N, dtype=np.int64) - ptr[pt_idx]
+    cam_idx = first[pt_idx] + within
+    return _finish(rng, cams, pts, cam_idx, pt_idx)
+
+
+def synthetic_clusters(num_cameras, num_points, num_observations, seed=38401, max_degree=48, cams_per_cluster=30):
+    """Venice-like photo collection: groups of cameras photograph the same facade from a wide arc; a point on a
+    facade is seen by `degree` distinct cameras of its group (10 % of the tracks also reach into the next group)."""
+    rng = np.random.RandomState(seed)
+    C, P, N = int(num_cameras), int(num_points), int(num_observations)
+    K = max(1, C // cams_per_cluster)
+    cl_of_cam = np.minimum(np.arange(C) * K // C, K - 1)
+    cl_start = np.searchsorted(cl_of_cam, np.arange(K))
+    cl_size = np.diff(np.concatenate([cl_start, [C]]))
+    max_degree = int(min(max_degree, cl_size.min()))
+    ang = 2.0 * np.pi * np.arange(K) / K
+    cl_center = 600.0 * np.stack([np.cos(ang), np.sin(ang), np.zeros(K)], axis=1)
+    cl_normal = np.stack([np.cos(ang), np.sin(ang), np.zeros(K)], axis=1)        # facade faces outward
+    cl_tangent = np.stack([-np.sin(ang), np.cos(ang), np.zeros(K)], axis=1)
+    kc = cl_of_cam
+    lateral = rng.uniform(-30.0, 30.0, C)
+    dist = rng.uniform(35.0, 70.0, C)
+    centers = cl_center[kc] + dist[:, None] * cl_normal[kc] + lateral[:, None] * cl_tangent[kc]
+    centers[:, 2] += rng.uniform(-3.0, 8.0, C)
+    targets = cl_center[kc] + rng.normal(0.0, 3.0, (C, 1)) * cl_tangent[kc]
+    cams = _look_at_cameras(centers, targets, rng)
+    deg = _degrees(rng, P, N, max_degree)
+    kp = np.sort(rng.randint(0, K, P))                                            # points grouped by facade
+    pts = cl_center[kp] + rng.uniform(-20.0, 20.0, P)[:, None] * cl_tangent[kp] + rng.normal(0.0, 1.5, P)[:, None] * cl_normal[kp]
+    pts[:, 2] += rng.uniform(-8.0, 12.0, P)
+    pt_idx = np.repeat(np.arange(P, dtype=np.int64), deg)
+    ptr = np.concatenate([[0], np.cumsum(deg)])
+    within = np.arange(N, dtype=np.int64) - ptr[pt_idx]
+    # `degree` distinct cameras of the group: evenly spaced with a random phase, then a random rotation of the group
+    size = cl_size[kp][pt_idx]
+    phase = rng.uniform(0.0, 1.0, P)[pt_idx]
+    rot = rng.randint(0, 1 << 20, P)[pt_idx]
+    local = (np.floor((within + phase) * (size / deg[pt_idx])).astype(np.int64) + rot) % size
+    cam_idx = cl_start[kp][pt_idx] + local
+    return _finish(rng, cams, pts, cam_idx, pt_idx)
+
+
+GENERATORS = {
+    "ladybug-1723": synthetic_sequence,   # video sequence
+    "trafalgar-257": synthetic_clusters,
+    "venice-1778": synthetic_clusters,    # photo collection
+    "tiny": synthetic_bal,
+    "ladybug-1723-random": synthetic_bal,  # worst case for locality: every point sees cameras all over the index range
+    "venice-1778-random": synthetic_bal,
+}
+
+
 def synthetic(name, seed=38401):
-    C, P, N = SHAPES[name]
-    return synthetic_bal(C, P, N, seed=seed)
+    C, P, N = SHAPES[name.replace("-random", "")]
+    return GENERATORS[name](C, P, N, seed=seed)
 
 
 def write_bal(bal, path):

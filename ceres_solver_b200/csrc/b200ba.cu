@@ -27,7 +27,9 @@
 
 #include "../../include/b200ba.h"
 #include "kernels.cuh"
+#include "kernels_v2.cuh"
 #include "vector_kernels.cuh"
+#include "cg_kernel.cuh"
 
 using namespace b200;
 
@@ -67,6 +69,8 @@ enum KernelId {
   K_JTJ,
   K_SCHUR_INIT,
   K_SCHUR_MUL,
+  K_SCHUR_MUL_BIG,
+  K_CAM_REDUCE,
   K_DIAG_BLOCKS,
   K_INVERT9,
   K_BACKSUB,
@@ -78,7 +82,7 @@ enum KernelId {
 };
 const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squared_column_norm", "scale_columns",
                                      "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
-                                     "schur_multiply", "schur_diag_blocks", "invert_9x9", "back_substitute",
+                                     "schur_multiply", "schur_multiply_big_points", "camera_reduce", "schur_diag_blocks", "invert_9x9", "back_substitute",
                                      "model_cost", "cg_vector", "lm_vector", "misc"};
 
 #ifdef B200_WITH_NCCL
@@ -157,6 +161,19 @@ struct b200_handle {
   double* h_scalars = nullptr;
   CgState* h_cg = nullptr;
   int* h_fail = nullptr;
+  // v2 (warp-tile, shared-memory-privatised camera vector) path
+  bool v2_ok = false;
+  V2View v2{};
+  ProblemView view_big{};   // CTA tiles holding only the points with more than 32 rows
+  int num_big_tiles = 0;
+  WarpTile* d_wtiles = nullptr;
+  uint32_t* d_row_meta = nullptr;
+  int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
+  double* d_partials = nullptr;
+  size_t v2_smem = 0;
+  double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
+  double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
+  int cg_grid = 1;
   // launch geometry
   int grid_tile[K_COUNT];
   // stats
@@ -328,19 +345,39 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
   return B200_OK;
 }
 
-// y = S x on device vectors [9C]; y is overwritten.  `done` (device int*) lets CG kernels turn the launch into a no-op.
-int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, bool seed_done_by_caller) {
+// y = S x on device vectors [9C]; y is overwritten.  done_flag (device int*, may be null) turns every launch into a
+// no-op once the PCG has terminated.
+int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* done_flag) {
   const double* Df = h->cur_D != nullptr ? h->cur_D + 3 * static_cast<size_t>(h->P) : nullptr;
-  if (!seed_done_by_caller) {
-    const bool seed = (h->rank == 0);
+  const double* seed = (h->rank == 0) ? Df : nullptr;
+  const int n = 9 * h->C;
+  if (h->v2_ok) {
+    if (h->v2.direct)
+      OK(launch(h, K_MISC, [&] {
+        diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
+      }));
+    OK(launch(h, K_SCHUR_MUL, [&] {
+      schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
+    }));
+    if (!h->v2.direct)
+      OK(launch(h, K_CAM_REDUCE, [&] {
+        cam_reduce_kernel<<<(n + 63) / 64, 256, h->v2.num_ctas * sizeof(int2), h->stream>>>(
+            n, h->v2.num_ctas, h->d_cta_cam, h->d_partials, 9 * h->v2.max_cam_span, seed, d_x, d_y, 0, done_flag);
+      }));
+    if (h->num_big_tiles > 0)
+      OK(launch(h, K_SCHUR_MUL_BIG, [&] {
+        schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
+            h->view_big, h->d_ete_inv, d_x, d_y, done_flag);
+      }));
+  } else {
     OK(launch(h, K_MISC, [&] {
-      diag_sq_mul_kernel<<<flat_grid(h, 9 * static_cast<size_t>(h->C), 256), 256, 0, h->stream>>>(9 * h->C, seed ? Df : nullptr, d_x, d_y);
+      diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
+    }));
+    OK(launch(h, K_SCHUR_MUL, [&] {
+      schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, d_x, d_y, done_flag);
     }));
   }
-  OK(launch(h, K_SCHUR_MUL, [&] {
-    schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, d_x, d_y, nullptr);
-  }));
-  return allreduce_sum(h, d_y, 9 * static_cast<size_t>(h->C));
+  return allreduce_sum(h, d_y, n);
 }
 
 int precond_update_dev(b200_handle* h, int type) {
@@ -376,8 +413,46 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   prm.r_tolerance = o->r_tolerance;
   const double* Df = d_D != nullptr ? d_D + 3 * static_cast<size_t>(h->P) : nullptr;
   const int precond = o->preconditioner_type == B200_PRECOND_IDENTITY ? 0 : 1;
-  const int seed = (h->rank == 0) ? 1 : 0;
-  OK(launch(h, K_CG_VEC, [&] { cg_begin_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, h->d_rhs, h->d_sol, h->d_r, h->d_cg); }));
+  CgVecArgs va{};
+  va.prm = prm;
+  va.C = h->C;
+  va.precond = precond;
+  va.minv = h->d_minv;
+  va.rhs = h->d_rhs;
+  va.x = h->d_sol;
+  va.r = h->d_r;
+  va.z = h->d_z;
+  va.p = h->d_p;
+  va.red = h->d_red;
+  va.st = h->d_cg;
+  // In direct-flush mode the vector kernel pre-seeds the next product's output (D_f^2 p, rank 0 only) and the product
+  // kernels RED straight into it: one product launch + one vector launch per iteration.
+  const bool seeded = h->v2_ok && h->v2.direct;
+  va.Df = (h->rank == 0) ? Df : nullptr;
+  auto vec = [&](int mode, double* q, double* seed_target) -> int {
+    va.mode = mode;
+    va.q = q;
+    va.seed_target = seeded ? seed_target : nullptr;
+    void* args[] = {&va};
+    return launch(h, K_CG_VEC, [&] {
+      cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
+    });
+  };
+  auto product = [&](const double* vin, double* out) -> int {
+    if (seeded) {
+      OK(launch(h, K_SCHUR_MUL, [&] {
+        schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
+      }));
+      if (h->num_big_tiles > 0)
+        OK(launch(h, K_SCHUR_MUL_BIG, [&] {
+          schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
+              h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
+        }));
+      return allreduce_sum(h, out, n);
+    }
+    return schur_mul_dev(h, vin, out, &h->d_cg->done);
+  };
+  OK(vec(CG_BEGIN, h->d_z, h->d_z));
   const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
   // Termination is decided on the device; the host only polls the state every few iterations
   // (kernels become no-ops once done is set), so there is no per-iteration synchronisation.
@@ -388,26 +463,14 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   while (!done) {
     for (int k = 0; k < check_every && it < max_it; ++k) {
       ++it;
-      OK(launch(h, K_CG_VEC, [&] {
-        cg_pre_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, precond, h->d_minv, Df, seed, h->d_r, h->d_z, h->d_p, h->d_z, h->d_cg);
-      }));
       // q aliases z exactly like the reference (conjugate_gradients_solver.h:193): z is dead once p is updated.
-      OK(launch(h, K_SCHUR_MUL, [&] {
-        schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, h->d_p, h->d_z, &h->d_cg->done);
-      }));
-      OK(allreduce_sum(h, h->d_z, n));
+      OK(product(h->d_p, h->d_z));
       if (it % reset == 0) {
-        OK(launch(h, K_CG_VEC, [&] {
-          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 1, h->d_rhs, nullptr, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
-        }));
-        OK(schur_mul_dev(h, h->d_sol, h->d_tmp, false));
-        OK(launch(h, K_CG_VEC, [&] {
-          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 2, h->d_rhs, h->d_tmp, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
-        }));
+        OK(vec(CG_RESET_FIRST, h->d_z, h->d_tmp));
+        OK(product(h->d_sol, h->d_tmp));
+        OK(vec(CG_RESET_SECOND, h->d_tmp, h->d_z));
       } else {
-        OK(launch(h, K_CG_VEC, [&] {
-          cg_post_kernel<<<1, kVecThreads, 0, h->stream>>>(prm, 0, h->d_rhs, nullptr, h->d_sol, h->d_r, h->d_p, h->d_z, h->d_cg);
-        }));
+        OK(vec(CG_NORMAL, h->d_z, h->d_z));
       }
     }
     CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
@@ -543,6 +606,88 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       tiles.push_back(t);
     }
   }
+  // v2 structures: warp tiles (whole points, <= 32 rows) for the points with <= 32 rows; points with 33..kTile
+  // rows stay on the CTA-tile kernels (one tile each).  Needs every point to have at least one row.
+  std::vector<WarpTile> wtiles;
+  std::vector<TileDesc> big_tiles;
+  std::vector<uint32_t> row_meta(static_cast<size_t>(N));
+  bool v2_possible = getenv("B200_DISABLE_V2") == nullptr;
+  for (int k = 0; k < P && v2_possible; ++k)
+    if (pt_ptr[k + 1] == pt_ptr[k]) v2_possible = false;
+  if (v2_possible) {
+    for (int k = 0; k < P; ++k)
+      for (int r = pt_ptr[k]; r < pt_ptr[k + 1]; ++r)
+        row_meta[r] = static_cast<uint32_t>(desc->cam_idx[r]) | (r == pt_ptr[k] ? 0x80000000u : 0u);
+    int k = 0;
+    while (k < P) {
+      const int deg0 = pt_ptr[k + 1] - pt_ptr[k];
+      if (deg0 > 32) {
+        TileDesc t;
+        t.pt_begin = k;
+        t.obs_begin = pt_ptr[k];
+        t.obs_count = deg0;
+        t.pt_count = 1;
+        big_tiles.push_back(t);
+        ++k;
+        continue;
+      }
+      WarpTile t;
+      t.row_begin = pt_ptr[k];
+      t.pt_begin = k;
+      int rows = 0, pts = 0;
+      while (k < P) {
+        const int deg = pt_ptr[k + 1] - pt_ptr[k];
+        if (deg > 32 || rows + deg > 32) break;
+        rows += deg;
+        ++pts;
+        ++k;
+      }
+      t.row_count = static_cast<unsigned short>(rows);
+      t.pt_count = static_cast<unsigned short>(pts);
+      wtiles.push_back(t);
+    }
+  }
+  const int num_ctas_v2 = prop.multiProcessorCount;
+  std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2);
+  int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1;
+  if (v2_possible && !wtiles.empty()) {
+    const long T = static_cast<long>(wtiles.size());
+    for (int b = 0; b < num_ctas_v2; ++b) {
+      const int t0 = static_cast<int>(T * b / num_ctas_v2), t1 = static_cast<int>(T * (b + 1) / num_ctas_v2);
+      cta_part[b] = make_int2(t0, t1);
+      int lo = C, hi = 0;
+      for (int t = t0; t < t1; ++t)
+        for (int r = wtiles[t].row_begin; r < wtiles[t].row_begin + wtiles[t].row_count; ++r) {
+          lo = std::min(lo, desc->cam_idx[r]);
+          hi = std::max(hi, desc->cam_idx[r] + 1);
+        }
+      if (hi <= lo) { lo = 0; hi = 0; }
+      cta_cam[b] = make_int2(lo, hi);
+      max_cam_span = std::max(max_cam_span, hi - lo);
+    }
+    // Shared memory budget: `replicas` private camera vectors + per-warp {TMA ring of F cells, exchange scratch}.
+    // Prefer one replica per warp (no cross-warp contention) when the camera span of a CTA is small.
+    const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 1024;
+    const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
+    for (int stages = 3; stages >= 1 && v2_warps == 0; --stages) {
+      const long pw = v2_per_warp_bytes(stages, kV2Scratch);
+      long w = (total - sy1) / pw;                       // warps with a single shared copy
+      long wr = total / (pw + sy1);                      // warps with one copy each
+      const long cap = kV2MaxThreads / 32;
+      if (wr >= cap) {                                    // everything fits with per-warp copies
+        v2_warps = static_cast<int>(cap);
+        v2_replicas = v2_warps;
+        v2_stages = stages;
+      } else if (w >= (stages >= 2 ? 8 : 4)) {
+        v2_warps = static_cast<int>(std::min(w, cap));
+        v2_stages = stages;
+        v2_replicas = static_cast<int>(std::max<long>(1, std::min<long>(v2_warps, (total - v2_warps * pw) / sy1)));
+      }
+    }
+    if (v2_warps == 0) v2_possible = false;  // camera vector does not fit next to the tile buffers: v1 kernels
+  } else {
+    v2_possible = false;
+  }
 
   b200_handle* h = new b200_handle;
   h->device = desc->device;
@@ -612,6 +757,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   OK(dev_alloc(&h->d_tmp, 9 * static_cast<size_t>(C)));
   OK(dev_alloc(&h->d_sol, 9 * static_cast<size_t>(C)));
   OK(dev_alloc(&h->d_cg, 1));
+  OK(dev_alloc(&h->d_ybig, 9 * static_cast<size_t>(C)));
+  CU(cudaMemsetAsync(h->d_ybig, 0, sizeof(double) * 9 * C, h->stream));
+  CU(cudaMemsetAsync(h->d_cg, 0, sizeof(CgState), h->stream));
   OK(dev_alloc(&h->d_scale, h->np));
   OK(dev_alloc(&h->d_sqnorm, h->np));
   OK(dev_alloc(&h->d_diagonal, h->np));
@@ -640,6 +788,49 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->view.obs = h->d_obs;
   h->view.values = h->d_values;
 
+  if (v2_possible) {
+    h->num_big_tiles = static_cast<int>(big_tiles.size());
+    TileDesc* d_big = nullptr;
+    OK(dev_alloc(&d_big, big_tiles.size()));
+    h->view_big = h->view;
+    h->view_big.tiles = d_big;
+    h->view_big.num_tiles = h->num_big_tiles;
+    OK(dev_alloc(&h->d_wtiles, wtiles.size()));
+    OK(dev_alloc(&h->d_row_meta, n));
+    OK(dev_alloc(&h->d_cta_part, cta_part.size()));
+    OK(dev_alloc(&h->d_cta_cam, cta_cam.size()));
+    OK(dev_alloc(&h->d_partials, static_cast<size_t>(num_ctas_v2) * 9 * max_cam_span));
+    if (!big_tiles.empty())
+      CU(cudaMemcpyAsync(d_big, big_tiles.data(), big_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_wtiles, wtiles.data(), wtiles.size() * sizeof(WarpTile), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_row_meta, row_meta.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_cta_part, cta_part.data(), cta_part.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_cta_cam, cta_cam.data(), cta_cam.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->v2.p = h->view;
+    h->v2.wtiles = h->d_wtiles;
+    h->v2.row_meta = h->d_row_meta;
+    h->v2.cta_part = h->d_cta_part;
+    h->v2.cta_cam = h->d_cta_cam;
+    h->v2.partials = h->d_partials;
+    h->v2.num_ctas = num_ctas_v2;
+    h->v2.max_cam_span = max_cam_span;
+    h->v2.warps = v2_warps;
+    h->v2.stages = v2_stages;
+    h->v2.replicas = v2_replicas;
+    {
+      long flush = 0;
+      for (int b = 0; b < num_ctas_v2; ++b) flush += 9L * (cta_cam[b].y - cta_cam[b].x);
+      h->v2.direct = (flush <= 400000) ? 1 : 0;   // <= ~4 us of REDs at the measured 95 G lane-RED/s
+    }
+    h->v2.per_warp_bytes = v2_per_warp_bytes(v2_stages, kV2Scratch);
+    h->v2_smem = v2_sy_bytes(max_cam_span, v2_replicas) + static_cast<size_t>(v2_warps) * h->v2.per_warp_bytes;
+    // function attributes are process-wide: always raise them to the device limit, never to this handle's need
+    CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin)));
+    CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin)));
+    h->v2_ok = true;
+  }
+
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -652,6 +843,13 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->grid_tile[K_DIAG_BLOCKS] = tile_grid(h, diag_blocks_kernel<true>, tile_smem_bytes<1, 1>());
   h->grid_tile[K_BACKSUB] = tile_grid(h, backsub_kernel, tile_smem_bytes<3, 1>());
   h->grid_tile[K_MODEL_COST] = tile_grid(h, model_cost_kernel, tile_smem_bytes<1, 1>());
+  {
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_vector_kernel, kCgThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int nblocks = (C + kCgCamsPerCta - 1) / kCgCamsPerCta;
+    h->cg_grid = std::max(1, std::min(nblocks, per_sm * h->sm_count));
+    OK(dev_alloc(&h->d_red, static_cast<size_t>(h->cg_grid) * 4));
+  }
 
   // Algorithmic (compulsory) bytes per launch, SURVEY §8d with this layout: J values 192 B/row + 4 B camera
   // index per row + 4 B chunk boundary per point, plus the vectors each kernel must read/write once.
@@ -682,7 +880,9 @@ void b200_destroy(b200_handle* h) {
                       h->d_residuals, h->d_gradient, h->d_tile_partial, h->d_fail, h->d_scalars, h->d_partial,
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
-                      h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y};
+                      h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_partials, h->d_ybig, h->d_red,
+                      const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -776,13 +976,33 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
   if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
   const double* dD = D != nullptr ? h->d_D : nullptr;
   const size_t off = 3 * static_cast<size_t>(h->P);
-  OK(launch(h, K_MISC, [&] {
-    diag_sq_mul_kernel<<<flat_grid(h, 9 * static_cast<size_t>(h->C), 256), 256, 0, h->stream>>>(
-        9 * h->C, (dD != nullptr && h->rank == 0) ? dD + off : nullptr, h->d_vp0 + off, h->d_vp1 + off);
-  }));
-  OK(launch(h, K_JTJ, [&] {
-    jtmul_kernel<true><<<h->grid_tile[K_JTJ], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_vp0, dD, h->d_vp1);
-  }));
+  const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
+  const int nc = 9 * h->C;
+  if (h->v2_ok) {
+    if (h->v2.direct)
+      OK(launch(h, K_MISC, [&] {
+        diag_sq_mul_kernel<<<flat_grid(h, nc, 256), 256, 0, h->stream>>>(nc, seedD, h->d_vp0 + off, h->d_vp1 + off, nullptr);
+      }));
+    OK(launch(h, K_JTJ, [&] {
+      jtj_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_vp0, dD, h->d_vp1);
+    }));
+    if (!h->v2.direct)
+      OK(launch(h, K_CAM_REDUCE, [&] {
+        cam_reduce_kernel<<<(nc + 63) / 64, 256, h->v2.num_ctas * sizeof(int2), h->stream>>>(
+            nc, h->v2.num_ctas, h->d_cta_cam, h->d_partials, 9 * h->v2.max_cam_span, seedD, h->d_vp0 + off, h->d_vp1 + off, 0, nullptr);
+      }));
+    if (h->num_big_tiles > 0)
+      OK(launch(h, K_JTJ, [&] {
+        jtmul_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, h->d_vp0, dD, h->d_vp1);
+      }));
+  } else {
+    OK(launch(h, K_MISC, [&] {
+      diag_sq_mul_kernel<<<flat_grid(h, nc, 256), 256, 0, h->stream>>>(nc, seedD, h->d_vp0 + off, h->d_vp1 + off, nullptr);
+    }));
+    OK(launch(h, K_JTJ, [&] {
+      jtmul_kernel<true><<<h->grid_tile[K_JTJ], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_vp0, dD, h->d_vp1);
+    }));
+  }
   OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
   return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
 }
@@ -844,7 +1064,7 @@ int b200_schur_multiply(b200_handle* h, const double* x, double* y) {
   if (h == nullptr || x == nullptr || y == nullptr || !h->schur_ready) return fail(B200_ERR_INVALID_ARGUMENT, "b200_schur_init first");
   CU(cudaSetDevice(h->device));
   OK(h2d(h, h->d_xr, x, sizeof(double) * 9 * h->C));
-  OK(schur_mul_dev(h, h->d_xr, h->d_tmp, false));
+  OK(schur_mul_dev(h, h->d_xr, h->d_tmp, nullptr));
   return d2h(h, y, h->d_tmp, sizeof(double) * 9 * h->C);
 }
 int b200_schur_back_substitute(b200_handle* h, const double* z, double* y) {

@@ -1,0 +1,436 @@
+// Warp-tile kernels (v2): the camera-scatter kernels re-designed around what the B200 measurements say
+// (profiles/r01_microbench_atomics_gather_stream.txt):
+//   * FP64 global RED tops out at ~95 G lane-ops/s chip-wide, regardless of locality -> 9 REDs per row make
+//     S*x RED-bound at ~29 % of the HBM roofline (profiles/r01_v1_schur_mul_ncu_details.txt);
+//   * FP64 atomics on SHARED memory (ATOMS.CAST.SPIN.64) sustain ~430 G lane-ops/s;
+//   * a TMA bulk-copy ring streams HBM at 7.2 TB/s.
+// So: one persistent CTA per SM keeps a PRIVATE copy of the camera-sized output in shared memory, rows are
+// processed in warp-sized tiles (whole points, <= 32 rows) so that the per-point reduction needs only
+// __syncwarp (no CTA barrier anywhere in the main loop), every warp runs its own TMA ring for the 2x9 F
+// cells (E cells are read straight from global: a warp's 32 cells are one contiguous 1.5 KB run), and the
+// per-CTA partial vectors are summed in a fixed order by a tiny second kernel (no global atomics at all).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct WarpTile {
+  int row_begin;
+  int pt_begin;
+  unsigned short row_count;  // <= 32
+  unsigned short pt_count;   // <= 32, every point has >= 1 row
+};
+
+struct V2View {
+  ProblemView p;
+  const WarpTile* wtiles;
+  const uint32_t* row_meta;  // [N] camera | (first row of its point ? 1u << 31 : 0)
+  const int2* cta_part;      // per CTA: [tile_begin, tile_end)
+  const int2* cta_cam;       // per CTA: [cam_lo, cam_hi) touched by its tiles
+  double* partials;          // [num_ctas][9 * max_cam_span]
+  int num_ctas;
+  int max_cam_span;
+  int warps;                 // warps per CTA
+  int stages;                // TMA ring depth per warp
+  int replicas;              // copies of the private camera vector (warp w uses copy w % replicas)
+  int direct;                // 1: CTAs RED their (narrow) camera range straight into the output vector; 0: partials
+  int per_warp_bytes;
+};
+
+constexpr int kV2MaxThreads = 384;
+constexpr int kV2Scratch = 3;  // doubles of per-lane exchange scratch in every v2 kernel
+
+__host__ __device__ inline int v2_per_warp_bytes(int stages, int scratch_doubles_per_lane) {
+  return (stages * 32 * 144 + 32 * scratch_doubles_per_lane * 8 + 8 * stages + 15) & ~15;
+}
+__host__ __device__ inline size_t v2_sy_stride(int max_cam_span) {  // doubles per replica
+  return (static_cast<size_t>(9) * max_cam_span + 15) & ~static_cast<size_t>(15);
+}
+__host__ __device__ inline size_t v2_sy_bytes(int max_cam_span, int replicas) {
+  return v2_sy_stride(max_cam_span) * 8 * replicas;
+}
+
+// Per-warp context: F ring, scratch, barriers.
+struct WarpCtx {
+  double* sF;
+  double* sW;
+  uint64_t* bars;
+};
+
+__device__ __forceinline__ WarpCtx v2_warp_ctx(const V2View& v, unsigned char* smem, int scratch_per_lane) {
+  const int warp = threadIdx.x >> 5;
+  unsigned char* base = smem + v2_sy_bytes(v.max_cam_span, v.replicas) + static_cast<size_t>(warp) * v.per_warp_bytes;
+  WarpCtx c;
+  c.sF = reinterpret_cast<double*>(base);
+  c.sW = c.sF + v.stages * 576;
+  c.bars = reinterpret_cast<uint64_t*>(c.sW + 32 * scratch_per_lane);
+  return c;
+}
+
+__device__ __forceinline__ void v2_issue(const V2View& v, const WarpCtx& c, int tile, int stage) {
+  const WarpTile wt = v.wtiles[tile];
+  const uint32_t bytes = wt.row_count * 144u;
+  mbar_arrive_expect_tx(c.bars + stage, bytes);
+  bulk_g2s(c.sF + stage * 576, v.p.F() + 18 * static_cast<size_t>(wt.row_begin), bytes, c.bars + stage);
+}
+
+// Segment bookkeeping inside a warp tile from the per-row head flags.
+struct Seg {
+  int first;     // first lane of my point
+  int end;       // one past the last lane of my point
+  int lpt;       // index of my point inside the tile
+};
+__device__ __forceinline__ Seg v2_segment(bool head, int row_count) {
+  const int lane = threadIdx.x & 31;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const unsigned le = heads & (0xffffffffu >> (31 - lane));
+  const unsigned gt = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+  Seg s;
+  s.first = 31 - __clz(le | 1u);
+  s.end = gt ? (__ffs(gt) - 1) : row_count;
+  s.lpt = __popc(le) - 1;
+  return s;
+}
+
+// Common prologue: zero the private camera vector, arm the barriers, prime the TMA ring.
+__device__ __forceinline__ void v2_prologue(const V2View& v, double* sy, const WarpCtx& c, int2 part, int2 cr,
+                                            int& t_issue) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  (void)cr;
+  const int n = static_cast<int>(v2_sy_stride(v.max_cam_span)) * v.replicas;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = 0.0;
+  if (lane == 0) {
+    for (int s = 0; s < v.stages; ++s) mbar_init(c.bars + s, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  t_issue = part.x + warp;
+  if (lane == 0) {
+    for (int s = 0; s < v.stages && t_issue < part.y; ++s) {
+      v2_issue(v, c, t_issue, s);
+      t_issue += v.warps;
+    }
+  } else {
+    for (int s = 0; s < v.stages && t_issue < part.y; ++s) t_issue += v.warps;
+  }
+}
+
+// Flush of the CTA-private camera vector.  With camera locality a CTA touches a few dozen cameras, so it adds its
+// range straight into the (pre-seeded) output with a few hundred REDs; otherwise (every CTA touches every camera)
+// it writes a partial vector that cam_reduce_kernel sums in a fixed order.
+__device__ __forceinline__ void v2_epilogue(const V2View& v, const double* sy, int2 cr, double* y_direct) {
+  __syncthreads();
+  const int n = 9 * (cr.y - cr.x);
+  const int stride = static_cast<int>(v2_sy_stride(v.max_cam_span));
+  double* dst = v.partials + static_cast<size_t>(blockIdx.x) * 9 * v.max_cam_span;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = sy[i];
+    for (int r = 1; r < v.replicas; ++r) acc += sy[r * stride + i];
+    if (v.direct) {
+      if (acc != 0.0) red_add(y_direct + 9 * static_cast<size_t>(cr.x) + i, acc);
+    } else {
+      dst[i] = acc;
+    }
+  }
+}
+
+// Accumulate one 9-vector per row into the CTA-private camera vector.
+//  1. rows of the warp that hit the same camera are summed through shuffles first (binary tree over the rank inside
+//     each __match_any group): with the camera locality of real captures a warp tile touches a handful of cameras,
+//     and un-aggregated lanes would fight over the same shared-memory words (measured: 3x slower than random data);
+//  2. the group leaders add into replica `rep` of the vector (one replica per warp when shared memory allows, so
+//     different warps never collide) with shared-memory FP64 atomics (ATOMS.CAST.SPIN.64, ~430 G lane-ops/s).
+__device__ __forceinline__ void cam_accumulate9(double* sy_rep, int cam_local, bool active, double (&g)[9]) {
+  const int lane = threadIdx.x & 31;
+  const int key = active ? cam_local : (0x40000000 | lane);
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  const int rank = __popc(m & ((1u << lane) - 1u));
+  const int n = __popc(m);
+  const int nmax = __reduce_max_sync(0xffffffffu, n);
+  for (int stride = 1; stride < nmax; stride <<= 1) {
+    const int src_rank = rank + stride;
+    const bool pull = ((rank & (2 * stride - 1)) == 0) && (src_rank < n);
+    const int src = pull ? static_cast<int>(__fns(m, 0, src_rank + 1)) : lane;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double v = __shfl_sync(0xffffffffu, g[k], src);
+      if (pull) g[k] += v;
+    }
+  }
+  if (active && rank == 0) {
+    double* yc = sy_rep + 9 * cam_local;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) atomicAdd(yc + k, g[k]);
+  }
+}
+
+// Row data of one warp tile that does not come through the TMA ring; loaded one tile ahead.
+struct RowPre {
+  WarpTile wt;
+  uint32_t meta;
+  double2 e0, e1, e2;
+};
+
+__device__ __forceinline__ void v2_load_row(const V2View& v, int tile, int tile_end, RowPre& r) {
+  const int lane = threadIdx.x & 31;
+  if (tile < tile_end) {
+    r.wt = v.wtiles[tile];
+    if (lane < r.wt.row_count) {
+      const size_t row = static_cast<size_t>(r.wt.row_begin) + lane;
+      r.meta = __ldg(v.row_meta + row);
+      const double2* ep = reinterpret_cast<const double2*>(v.p.E() + 6 * row);
+      r.e0 = __ldg(ep);
+      r.e1 = __ldg(ep + 1);
+      r.e2 = __ldg(ep + 2);
+    } else {
+      r.meta = 0u;
+      r.e0 = r.e1 = r.e2 = make_double2(0.0, 0.0);
+    }
+  } else {
+    r.wt.row_begin = 0;
+    r.wt.pt_begin = 0;
+    r.wt.row_count = 0;
+    r.wt.pt_count = 0;
+    r.meta = 0u;
+    r.e0 = r.e1 = r.e2 = make_double2(0.0, 0.0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// partial_y(camera part) = F'(F x - E (E'E+D^2)^-1 E'F x)     x: [9C]
+// Software pipeline per warp: the F cells of tile i+1.. are in flight in the TMA ring, the E cells / row meta of
+// tile i+1 are loaded before tile i's arithmetic, and the x / (E'E)^-1 gathers of tile i+1 are issued before
+// tile i's shared-memory accumulation, so every global latency overlaps work of the previous tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kV2MaxThreads, 1)
+    schur_mul_v2_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
+                        const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sy = reinterpret_cast<double*>(smem_raw);
+  const WarpCtx c = v2_warp_ctx(v, smem_raw, kV2Scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = v.cta_part[blockIdx.x];
+  const int2 cr = v.cta_cam[blockIdx.x];
+  int t_issue;
+  v2_prologue(v, sy, c, part, cr, t_issue);
+
+  RowPre cur, nxt;
+  double xc[9], pinv[6], xn[9], pn[6];
+  v2_load_row(v, part.x + warp, part.y, cur);
+  bool active = lane < cur.wt.row_count;
+  int cam = static_cast<int>(cur.meta & 0x7fffffffu);
+  Seg sg = v2_segment(active && (cur.meta >> 31), cur.wt.row_count);
+  if (active) {
+    const double* xcp = x + 9 * static_cast<size_t>(cam);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+    const double* pi = ete_inv + 6 * static_cast<size_t>(cur.wt.pt_begin + sg.lpt);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pinv[k] = __ldg(pi + k);
+  }
+  int it = 0;
+  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
+    const int s = it % v.stages;
+    const uint32_t parity = (it / v.stages) & 1;
+    v2_load_row(v, tile + v.warps, part.y, nxt);  // E cells + meta of the next tile: in flight during this tile
+    mbar_wait(c.bars + s, parity);
+    double f[18];
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      const double* fr = c.sF + s * 576 + lane * 18;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(fr + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        t0 += f[k] * xc[k];
+        t1 += f[9 + k] * xc[k];
+      }
+      c.sW[lane * 3 + 0] = cur.e0.x * t0 + cur.e1.y * t1;
+      c.sW[lane * 3 + 1] = cur.e0.y * t0 + cur.e2.x * t1;
+      c.sW[lane * 3 + 2] = cur.e1.x * t0 + cur.e2.y * t1;
+    }
+    __syncwarp();
+    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      for (int j = sg.first; j < sg.end; ++j) {
+        u0 += c.sW[j * 3 + 0];
+        u1 += c.sW[j * 3 + 1];
+        u2 += c.sW[j * 3 + 2];
+      }
+      const double v0 = -(pinv[0] * u0 + pinv[1] * u1 + pinv[2] * u2);
+      const double v1 = -(pinv[1] * u0 + pinv[3] * u1 + pinv[4] * u2);
+      const double v2 = -(pinv[2] * u0 + pinv[4] * u1 + pinv[5] * u2);
+      t0 += cur.e0.x * v0 + cur.e0.y * v1 + cur.e1.x * v2;
+      t1 += cur.e1.y * v0 + cur.e2.x * v1 + cur.e2.y * v2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
+    }
+    // gathers for the next tile (depend on its meta, which was requested before this tile's arithmetic)
+    const bool nactive = lane < nxt.wt.row_count;
+    const int ncam = static_cast<int>(nxt.meta & 0x7fffffffu);
+    const Seg nsg = v2_segment(nactive && (nxt.meta >> 31), nxt.wt.row_count);
+    if (nactive) {
+      const double* xcp = x + 9 * static_cast<size_t>(ncam);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) xn[k] = __ldg(xcp + k);
+      const double* pi = ete_inv + 6 * static_cast<size_t>(nxt.wt.pt_begin + nsg.lpt);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pn[k] = __ldg(pi + k);
+    }
+    cam_accumulate9(sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span), cam - cr.x, active, g);
+    __syncwarp();
+    if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
+    t_issue += v.warps;
+    cur = nxt;
+    active = nactive;
+    cam = ncam;
+    sg = nsg;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) xc[k] = xn[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) pinv[k] = pn[k];
+  }
+  v2_epilogue(v, sy, cr, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// y = J'(J x) + D^2 x in one pass: point part written directly (owned by the tile), camera part -> partials.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kV2MaxThreads, 1)
+    jtj_v2_kernel(V2View v, const double* __restrict__ x, const double* __restrict__ D, double* y) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sy = reinterpret_cast<double*>(smem_raw);
+  const WarpCtx c = v2_warp_ctx(v, smem_raw, kV2Scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = v.cta_part[blockIdx.x];
+  const int2 cr = v.cta_cam[blockIdx.x];
+  int t_issue;
+  v2_prologue(v, sy, c, part, cr, t_issue);
+  const size_t off = 3 * static_cast<size_t>(v.p.P);
+  int it = 0;
+  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
+    const int s = it % v.stages;
+    const uint32_t parity = (it / v.stages) & 1;
+    const WarpTile wt = v.wtiles[tile];
+    const bool active = lane < wt.row_count;
+    const size_t row = static_cast<size_t>(wt.row_begin) + lane;
+    const uint32_t meta = active ? v.row_meta[row] : 0x80000000u;
+    const int cam = static_cast<int>(meta & 0x7fffffffu);
+    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    double xc[9], xp[3] = {0, 0, 0};
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    size_t po = 0;
+    if (active) {
+      const double* xcp = x + off + 9 * static_cast<size_t>(cam);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+      po = 3 * static_cast<size_t>(wt.pt_begin + sg.lpt);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xp[k] = __ldg(x + po + k);
+      const double2* ep = reinterpret_cast<const double2*>(v.p.E() + 6 * row);
+      e0 = __ldg(ep);
+      e1 = __ldg(ep + 1);
+      e2 = __ldg(ep + 2);
+    }
+    mbar_wait(c.bars + s, parity);
+    double f[18] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      const double* fr = c.sF + s * 576 + lane * 18;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(fr + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+      t0 = e0.x * xp[0] + e0.y * xp[1] + e1.x * xp[2];
+      t1 = e1.y * xp[0] + e2.x * xp[1] + e2.y * xp[2];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        t0 += f[k] * xc[k];
+        t1 += f[9 + k] * xc[k];
+      }
+      c.sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
+      c.sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
+      c.sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+    }
+    {
+      double g[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = active ? f[k] * t0 + f[9 + k] * t1 : 0.0;
+      cam_accumulate9(sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span), cam - cr.x, active, g);
+    }
+    __syncwarp();
+    if (active && lane == sg.first) {
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      for (int j = sg.first; j < sg.end; ++j) {
+        u0 += c.sW[j * 3 + 0];
+        u1 += c.sW[j * 3 + 1];
+        u2 += c.sW[j * 3 + 2];
+      }
+      if (D != nullptr) {
+        u0 += D[po] * D[po] * xp[0];
+        u1 += D[po + 1] * D[po + 1] * xp[1];
+        u2 += D[po + 2] * D[po + 2] * xp[2];
+      }
+      y[po] = u0;
+      y[po + 1] = u1;
+      y[po + 2] = u2;
+    }
+    __syncwarp();
+    if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
+    t_issue += v.warps;
+  }
+  v2_epilogue(v, sy, cr, y + off);
+}
+
+// ------------------------------------------------------------------------------------------------
+// y[j] = (seed ? d[j]^2 x[j] : 0) + sum over CTAs (fixed order) of their partial for camera entry j.
+// add != 0: y[j] += ... instead (accumulate on top of an existing vector).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    cam_reduce_kernel(int n, int num_ctas, const int2* __restrict__ cta_cam, const double* __restrict__ partials,
+                      int stride, const double* __restrict__ d, const double* __restrict__ x, double* y, int add,
+                      const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  // 64 camera entries per block x 4 slices of the CTA list; slices are combined in a fixed order.
+  extern __shared__ int2 s_ranges[];
+  __shared__ double s_part[4][64];
+  for (int b = threadIdx.x; b < num_ctas; b += blockDim.x) s_ranges[b] = cta_cam[b];
+  __syncthreads();
+  const int e = threadIdx.x & 63, slice = threadIdx.x >> 6;
+  const int j = blockIdx.x * 64 + e;
+  double acc = 0.0;
+  if (j < n) {
+    const int cidx = j / 9;
+    const int b0 = num_ctas * slice / 4, b1 = num_ctas * (slice + 1) / 4;
+    double a0 = 0.0, a1 = 0.0;
+    int b = b0;
+    for (; b + 1 < b1; b += 2) {
+      const int2 r0 = s_ranges[b], r1 = s_ranges[b + 1];
+      if (cidx >= r0.x && cidx < r0.y) a0 += partials[static_cast<size_t>(b) * stride + (j - 9 * r0.x)];
+      if (cidx >= r1.x && cidx < r1.y) a1 += partials[static_cast<size_t>(b + 1) * stride + (j - 9 * r1.x)];
+    }
+    if (b < b1) {
+      const int2 r0 = s_ranges[b];
+      if (cidx >= r0.x && cidx < r0.y) a0 += partials[static_cast<size_t>(b) * stride + (j - 9 * r0.x)];
+    }
+    acc = a0 + a1;
+  }
+  s_part[slice][e] = acc;
+  __syncthreads();
+  if (slice == 0 && j < n) {
+    double v = (d != nullptr) ? d[j] * d[j] * x[j] : 0.0;
+    if (add) v += y[j];
+    v += ((s_part[0][e] + s_part[1][e]) + (s_part[2][e] + s_part[3][e]));
+    y[j] = v;
+  }
+}
+
+}  // namespace b200

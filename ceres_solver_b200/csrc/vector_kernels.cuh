@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(kVecThreads)
 
 // y[i] = d[i]^2 * x[i]  (or 0 when d == nullptr)
 __global__ void __launch_bounds__(256) diag_sq_mul_kernel(int n, const double* __restrict__ d,
-                                                          const double* __restrict__ x, double* y) {
+                                                          const double* __restrict__ x, double* y,
+                                                          const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     y[i] = d != nullptr ? d[i] * d[i] * x[i] : 0.0;

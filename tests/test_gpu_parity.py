@@ -197,10 +197,14 @@ def test_schur_solve_matches_oracle(precond, c16_case, cs):
     # |r| <= 1e-10 |b| sits at the rounding floor of the recurrence, so the exact stopping iteration depends on
     # summation order (the reference's own threaded runs differ the same way); the solutions must still agree.
     assert abs(its - its_o) <= max(3, its_o // 10)
-    assert relerr(x, x_o) < 1e-7
+    # both stop at |r| <= 1e-10 |b|; how far that is from the exact solution depends on the conditioning of the
+    # preconditioned system (worst with IDENTITY), so compare both against the exact (dense Schur) solve
     x_exact, _, _ = J.linear_solve(case.gpu.P, b, D, solver=1, nt=8)
+    tol = 1e-7 if precond != 0 else 2e-5
+    assert relerr(x, x_o) < tol
     if term == cs.LS_SUCCESS:
-        assert relerr(x, x_exact) < 1e-6
+        assert relerr(x, x_exact) < 10 * tol
+        assert relerr(x_o, x_exact) < 10 * tol
 
 
 def test_schur_solve_max_iterations(c16_case, cs):
