@@ -137,6 +137,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     workload = args.workload or "ladybug-1723"
 
     if args.impl == "reference":
@@ -164,19 +166,35 @@ def main():
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    nccl_id = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if world > 1:
-        raise SystemExit("multi-GPU path is not wired into bench.py yet")
+        # the library runs its own communicator (one all-reduce of the camera-sized vector per CG iteration);
+        # torch.distributed is only the plumbing that hands the NCCL id to every rank and synchronises the timing
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(cs.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
 
     bal, desc = make_problem(workload)
     rp = B.ReducedProgram(bal)
-    state0 = rp.state(bal)
+    full_state = rp.state(bal)
     stream = torch.cuda.current_stream()
-    gpu = cs.Problem(rp.C, rp.P, rp.row_cam, rp.row_pt, rp.row_obs, device=local_rank, stream=stream.cuda_stream)
+    if world > 1:
+        # points (and all their rows) are sharded by observation count, cameras are replicated
+        plo, phi, rlo, rhi = rp.shard(rank, world)
+        gpu = cs.Problem(rp.C, phi - plo, rp.row_cam[rlo:rhi], rp.row_pt[rlo:rhi] - plo, rp.row_obs[rlo:rhi],
+                         device=local_rank, stream=stream.cuda_stream, rank=rank, world_size=world, nccl_id=nccl_id)
+        state0 = np.concatenate([full_state[3 * plo:3 * phi], full_state[3 * rp.P:]])
+    else:
+        gpu = cs.Problem(rp.C, rp.P, rp.row_cam, rp.row_pt, rp.row_obs, device=local_rank, stream=stream.cuda_stream)
+        state0 = full_state
 
     def timed_solve(iters, host_boundary):
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
@@ -184,12 +202,20 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        return e0.elapsed_time(e1) / 1e3, wall, recs
+        dev = e0.elapsed_time(e1) / 1e3
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([dev, wall], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)   # max over ranks
+            dev, wall = float(t[0]), float(t[1])
+        return dev, wall, recs
 
     # warm-up
+    single = world == 1
     if args.warmup > 0:
         timed_solve(args.warmup, False)
-        timed_solve(min(args.warmup, 2), True)
+        if single:
+            timed_solve(min(args.warmup, 2), True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     gpu.stats_reset()
@@ -198,8 +224,10 @@ def main():
     clocks = sampler.stop()
     iters = max(1, len(recs) - 1)
     # end to end through the host-buffer boundary
+    # (N > 1: the sharded problem has no host-buffer boundary; end to end is then the device-resident loop with
+    #  the state uploaded from / downloaded to host memory inside the timed call, wall clock, max over ranks)
     gpu.stats_reset()
-    e2e_dev_s, e2e_wall_s, recs_e2e = timed_solve(args.steps, True)
+    e2e_dev_s, e2e_wall_s, recs_e2e = timed_solve(args.steps, single)
     h2d, d2h = gpu.transfer_bytes()
     e2e_iters = max(1, len(recs_e2e) - 1)
     # per-kernel event timing for the roofline (same steps, instrumented)
@@ -210,7 +238,7 @@ def main():
     gpu.profile(False)
     peak, peak_src = load_peaks()
     total_ms = sum(v["ms"] for v in stats.values())
-    dom_name, dom = max(stats.items(), key=lambda kv: kv[1]["ms"])
+    dom_name, dom = max(((k, v) for k, v in stats.items() if v["bytes_per_launch"] > 0), key=lambda kv: kv[1]["ms"])
     achieved = dom["bytes_per_launch"] * dom["launches"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                    "share": round(v["ms"] / total_ms, 4) if total_ms > 0 else 0.0,
@@ -236,13 +264,21 @@ def main():
                          "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},
             "kernels": kernels,
             "final_cost": recs[-1]["cost"]}
-    if not args.no_cpu_baseline:
+    if world > 1:
+        line["config"]["sharding"] = "points sharded over %d ranks by observation count, cameras replicated; one NCCL all-reduce of the %d-double camera vector per CG iteration" % (world, 9 * rp.C)
+        if rank != 0:
+            gpu.close()
+            dist.destroy_process_group()
+            return 0
+    if not args.no_cpu_baseline and world == 1:
         r = run_reference(args, bal, desc)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                 "sample": "%d LM iterations from the same initial point (%d CG iterations), %.1f s" % (
                                     r["iterations"], sum(int(t["ls_iterations"]) for t in r["trace"]), r["seconds"])}
     print(json.dumps(line))
     gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
     return 0
 
 

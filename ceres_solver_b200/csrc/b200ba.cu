@@ -304,6 +304,14 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
   if (d_gradient != nullptr) OK(allreduce_sum(h, d_gradient + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
   OK(allreduce_sum(h, h->d_scalars, 1));
   CU(cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (h->world > 1) {  // a failure on any shard fails the evaluation on every rank
+    OK(launch(h, K_MISC, [&] { flag_to_double_kernel<<<1, 1, 0, h->stream>>>(h->d_fail, h->d_scalars + 2); }));
+#ifdef B200_WITH_NCCL
+    ncclResult_t r = g_nccl.AllReduce(h->d_scalars + 2, h->d_scalars + 2, 1, ncclDouble, ncclMax, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+#endif
+    OK(launch(h, K_MISC, [&] { double_to_flag_kernel<<<1, 1, 0, h->stream>>>(h->d_scalars + 2, h->d_fail); }));
+  }
   CU(cudaMemcpyAsync(h->h_fail, h->d_fail, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *cost_out = h->h_scalars[0];
@@ -490,11 +498,41 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   return B200_OK;
 }
 
-int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out) {
+int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks = false) {
   OK(launch(h, K_LM_VEC, [&] { reduce_final_kernel<<<1, 32, 0, h->stream>>>(blocks, slots, op_mask, h->d_partial, h->d_scalars + 8); }));
+#ifdef B200_WITH_NCCL
+  if (across_ranks && h->world > 1) {
+    for (int i = 0; i < slots; ++i) {
+      const ncclRedOp_t op = ((op_mask >> i) & 1u) ? ncclMax : ncclSum;
+      ncclResult_t r = g_nccl.AllReduce(h->d_scalars + 8 + i, h->d_scalars + 8 + i, 1, ncclDouble, op, h->comm, h->stream);
+      if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+    }
+  }
+#else
+  (void)across_ranks;
+#endif
   CU(cudaMemcpyAsync(h->h_scalars + 8, h->d_scalars + 8, sizeof(double) * slots, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < slots; ++i) host_out[i] = h->h_scalars[8 + i];
+  return B200_OK;
+}
+
+// Reduction over a [points | cameras] vector when the points are sharded across ranks and the cameras are
+// replicated: the point range is reduced locally and combined across ranks, the camera range is counted once.
+// run(offset, count) must launch the partial-producing kernel on that sub-range with `grid` blocks.
+template <typename L>
+int sharded_reduce(b200_handle* h, int grid, int slots, unsigned op_mask, double* out, L&& run) {
+  const int nP = 3 * h->P, nC = 9 * h->C;
+  if (h->world == 1) {
+    OK(run(0, nP + nC));
+    return reduce_partials(h, grid, slots, op_mask, out);
+  }
+  double pt[8], cam[8];
+  OK(run(0, nP));
+  OK(reduce_partials(h, grid, slots, op_mask, pt, true));
+  OK(run(nP, nC));
+  OK(reduce_partials(h, grid, slots, op_mask, cam));
+  for (int i = 0; i < slots; ++i) out[i] = ((op_mask >> i) & 1u) ? std::max(pt[i], cam[i]) : pt[i] + cam[i];
   return B200_OK;
 }
 
@@ -1103,6 +1141,8 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
   *num_records = 0;
+  if (host_boundary && h->world > 1)
+    return fail(B200_ERR_UNSUPPORTED, "the host-buffer boundary is single-GPU; sharded problems run the device-resident loop");
   const int np = h->np;
   const size_t nr = 2 * static_cast<size_t>(h->N);
   const size_t off = 3 * static_cast<size_t>(h->P);
@@ -1158,13 +1198,10 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
       OK(scale_dev(h, h->d_scale));
       have_scaling = true;
     }
-    OK(launch(h, K_LM_VEC, [&] { grad_norm_kernel<<<vgrid, 256, 0, h->stream>>>(np, h->d_gradient, h->d_partial); }));
     double gn[2];
-    OK(reduce_partials(h, vgrid, 2, 0x1u, gn));
-    if (h->world > 1) {
-      // point part is sharded: combine across ranks (max / sum of squares) with the camera part counted once
-      // (handled by the caller-side reduction in the multi-GPU driver; single-rank path needs nothing).
-    }
+    OK(sharded_reduce(h, vgrid, 2, 0x1u, gn, [&](int ofs, int cnt) {
+      return launch(h, K_LM_VEC, [&] { grad_norm_kernel<<<vgrid, 256, 0, h->stream>>>(cnt, h->d_gradient + ofs, h->d_partial); });
+    }));
     it.gradient_max_norm = gn[0];
     it.gradient_norm = std::sqrt(gn[1]);
     return B200_OK;
@@ -1238,11 +1275,13 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
         model_cost_change = -dot;
       } else {
         // step = -y, delta = step * scaling, candidate = x + delta and the norms, in one pass
-        OK(launch(h, K_LM_VEC, [&] {
-          lm_step_kernel<<<vgrid, 256, 0, h->stream>>>(np, h->d_y, h->d_scale, h->d_state, h->d_step, h->d_cand, h->d_partial);
-        }));
         double red[3];
-        OK(reduce_partials(h, vgrid, 3, 0u, red));
+        OK(sharded_reduce(h, vgrid, 3, 0u, red, [&](int ofs, int cnt) {
+          return launch(h, K_LM_VEC, [&] {
+            lm_step_kernel<<<vgrid, 256, 0, h->stream>>>(cnt, h->d_y + ofs, h->d_scale + ofs, h->d_state + ofs, h->d_step + ofs,
+                                                         h->d_cand + ofs, h->d_partial);
+          });
+        }));
         step_sq = red[0];
         x_sq = red[1];
         if (red[2] != 0.0) solver_ok = false;

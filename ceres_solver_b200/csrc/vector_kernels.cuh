@@ -224,6 +224,9 @@ __global__ void __launch_bounds__(256) diag_sq_mul_kernel(int n, const double* _
     y[i] = d != nullptr ? d[i] * d[i] * x[i] : 0.0;
 }
 
+__global__ void flag_to_double_kernel(const int* flag, double* out) { out[0] = flag[0] != 0 ? 1.0 : 0.0; }
+__global__ void double_to_flag_kernel(const double* in, int* flag) { flag[0] = in[0] != 0.0 ? 1 : 0; }
+
 __global__ void __launch_bounds__(256) fill_kernel(size_t n, double* y, double v) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = v;
