@@ -1,0 +1,161 @@
+// See b200_adapter.h.  Every C-ABI call is checked; failures map onto the reference's own error channels
+// (Evaluate -> false, Create -> nullptr + *error, Solve -> Summary::termination_type), never exceptions.
+#include "ceres/b200_adapter.h"
+
+#include <cmath>
+#include <vector>
+
+#include "absl/log/check.h"
+#include "absl/log/log.h"
+#include "ceres/autodiff_cost_function.h"
+#include "ceres/block_jacobian_writer.h"
+#include "ceres/loss_function.h"
+#include "ceres/parameter_block.h"
+#include "ceres/residual_block.h"
+#include "snavely_reprojection_error.h"  // examples/: the cost functor the device kernel implements
+
+namespace ceres::internal {
+namespace {
+using SnavelyCost = AutoDiffCostFunction<examples::SnavelyReprojectionError, 2, 9, 3>;
+
+bool Check(int rc, const char* what) {
+  if (rc == B200_OK) return true;
+  LOG(ERROR) << what << " failed: " << b200_last_error();
+  return false;
+}
+}  // namespace
+
+// ---------------------------------------------------------------- B200Jacobian
+void B200Jacobian::SquaredColumnNorm(double* x) const { CHECK(Check(b200_jacobian_squared_column_norm(handle(), x), "SquaredColumnNorm")); }
+void B200Jacobian::ScaleColumns(const double* scale) { CHECK(Check(b200_jacobian_scale_columns(handle(), scale), "ScaleColumns")); }
+void B200Jacobian::RightMultiplyAndAccumulate(const double* x, double* y) const {
+  CHECK(Check(b200_jacobian_right_multiply(handle(), x, y), "RightMultiplyAndAccumulate"));
+}
+void B200Jacobian::LeftMultiplyAndAccumulate(const double* x, double* y) const {
+  CHECK(Check(b200_jacobian_left_multiply(handle(), x, y), "LeftMultiplyAndAccumulate"));
+}
+
+// ---------------------------------------------------------------- B200Evaluator
+std::unique_ptr<Evaluator> B200Evaluator::Create(const Evaluator::Options& options, Program* program, std::string* error) {
+  const int P = options.num_eliminate_blocks;  // e blocks come first in the reduced program (reorder_program.cc:262-273)
+  const int C = program->NumParameterBlocks() - P;
+  const auto& residual_blocks = program->residual_blocks();
+  const int64_t N = static_cast<int64_t>(residual_blocks.size());
+  std::vector<int32_t> cam_idx(N), pt_idx(N);
+  std::vector<double> obs(2 * N);
+  int loss_type = B200_LOSS_TRIVIAL;
+  double loss_a = 1.0;
+  for (int64_t i = 0; i < N; ++i) {
+    const ResidualBlock* rb = residual_blocks[i];
+    const auto* cost = dynamic_cast<const SnavelyCost*>(rb->cost_function());
+    if (cost == nullptr || rb->NumParameterBlocks() != 2 || rb->parameter_blocks()[0]->Size() != 9 ||
+        rb->parameter_blocks()[1]->Size() != 3 || rb->parameter_blocks()[0]->manifold() != nullptr ||
+        rb->parameter_blocks()[1]->manifold() != nullptr) {
+      *error = "B200Evaluator: residual block " + std::to_string(i) + " is not SnavelyReprojectionError<2,9,3> on Euclidean (camera, point) blocks";
+      return nullptr;  // no silent CPU fallback on the hot path
+    }
+    const int cam_block = rb->parameter_blocks()[0]->index();  // index in the reduced program
+    const int pt_block = rb->parameter_blocks()[1]->index();
+    if (pt_block >= P || cam_block < P) {
+      *error = "B200Evaluator: points must form the first elimination group (linear_solver_ordering)";
+      return nullptr;
+    }
+    pt_idx[i] = pt_block;
+    cam_idx[i] = cam_block - P;
+    obs[2 * i] = cost->functor().observed_x;
+    obs[2 * i + 1] = cost->functor().observed_y;
+    if (const LossFunction* loss = rb->loss_function()) {
+      if (dynamic_cast<const HuberLoss*>(loss) == nullptr) {
+        *error = "B200Evaluator: only the trivial and Huber losses are implemented";
+        return nullptr;
+      }
+      double rho[3];
+      loss->Evaluate(1e8, rho);                 // outlier region: rho' = a / sqrt(s)   (loss_function.cc:52-66)
+      loss_type = B200_LOSS_HUBER;
+      loss_a = rho[1] * 1e4;
+    }
+  }
+  b200_ba_desc desc{};
+  desc.num_cameras = C;
+  desc.num_points = P;
+  desc.num_observations = N;
+  desc.cam_idx = cam_idx.data();
+  desc.pt_idx = pt_idx.data();
+  desc.obs = obs.data();
+  desc.loss_type = loss_type;
+  desc.loss_a = loss_a;
+  desc.device = 0;
+  desc.world_size = 1;
+  auto ctx = std::make_shared<B200Context>();
+  if (b200_create(&desc, &ctx->handle) != B200_OK) {
+    *error = std::string("B200Evaluator: ") + b200_last_error();
+    return nullptr;
+  }
+  return std::unique_ptr<Evaluator>(new B200Evaluator(program, std::move(ctx), P));
+}
+
+std::unique_ptr<SparseMatrix> B200Evaluator::CreateJacobian() const {
+  // Same block structure Ceres would build (block_jacobian_writer.cc:198-263) so DetectStructure and friends work.
+  Evaluator::Options opts;
+  opts.num_eliminate_blocks = num_eliminate_blocks_;
+  BlockJacobianWriter writer(opts, program_);
+  std::unique_ptr<SparseMatrix> plain = writer.CreateJacobian();
+  auto* bsm = down_cast<BlockSparseMatrix*>(plain.get());
+  auto* bs = new CompressedRowBlockStructure(*bsm->block_structure());
+  return std::make_unique<B200Jacobian>(bs, ctx_);
+}
+
+bool B200Evaluator::Evaluate(const Evaluator::EvaluateOptions&, const double* state, double* cost, double* residuals,
+                             double* gradient, SparseMatrix* jacobian) {
+  ScopedExecutionTimer total("Evaluator::Total", &execution_summary_);
+  ScopedExecutionTimer kind(gradient == nullptr && jacobian == nullptr ? "Evaluator::Residual" : "Evaluator::Jacobian",
+                            &execution_summary_);  // the keys Solver::Summary reads (solver.cc:615-628)
+  const int rc = b200_evaluate(ctx_->handle, state, cost, residuals, gradient, jacobian != nullptr);
+  if (rc == B200_ERR_EVALUATION_FAILED) return false;
+  return Check(rc, "b200_evaluate");
+}
+
+bool B200Evaluator::Plus(const double* state, const double* delta, double* state_plus_delta) const {
+  return b200_plus(ctx_->handle, state, delta, state_plus_delta) == B200_OK;
+}
+
+// ---------------------------------------------------------------- B200IterativeSchurSolver
+LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, const double* b,
+                                                          const LinearSolver::PerSolveOptions& per_solve_options,
+                                                          double* x) {
+  LinearSolver::Summary summary;
+  auto* jac = dynamic_cast<B200Jacobian*>(A);
+  if (jac == nullptr) {
+    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+    summary.message = "B200IterativeSchurSolver needs the Jacobian created by B200Evaluator.";
+    return summary;
+  }
+  b200_solver_options o;
+  b200_solver_options_default(&o);
+  switch (options_.preconditioner_type) {
+    case IDENTITY: o.preconditioner_type = B200_PRECOND_IDENTITY; break;
+    case JACOBI: o.preconditioner_type = B200_PRECOND_JACOBI; break;
+    case SCHUR_JACOBI: o.preconditioner_type = B200_PRECOND_SCHUR_JACOBI; break;
+    default:
+      summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+      summary.message = "Preconditioner not implemented on the B200 path.";
+      return summary;
+  }
+  o.min_num_iterations = options_.min_num_iterations;
+  o.max_num_iterations = options_.max_num_iterations;
+  o.residual_reset_period = options_.residual_reset_period;
+  o.q_tolerance = per_solve_options.q_tolerance;
+  o.r_tolerance = per_solve_options.r_tolerance;
+  b200_solver_summary s{};
+  if (b200_schur_solve(jac->handle(), b, per_solve_options.D, &o, x, &s) != B200_OK) {
+    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+    summary.message = b200_last_error();
+    return summary;
+  }
+  summary.num_iterations = s.num_iterations;
+  summary.residual_norm = s.residual_norm;
+  summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);  // same numeric order
+  return summary;
+}
+
+}  // namespace ceres::internal
