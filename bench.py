@@ -238,7 +238,11 @@ def main():
     gpu.profile(False)
     peak, peak_src = load_peaks()
     total_ms = sum(v["ms"] for v in stats.values())
-    dom_name, dom = max(((k, v) for k, v in stats.items() if v["bytes_per_launch"] > 0), key=lambda kv: kv[1]["ms"])
+    by_time = max(((k, v) for k, v in stats.items() if v["bytes_per_launch"] > 0), key=lambda kv: kv[1]["ms"])[0]
+    # the roofline line is about the kernel north_star names (the implicit-Schur product feeding CG), which is also
+    # the dominant kernel on the default workload; `dominant_kernel_by_time` says which HBM kernel took most time here
+    dom_name = "schur_multiply" if stats.get("schur_multiply", {}).get("launches", 0) > 0 else by_time
+    dom = stats[dom_name]
     achieved = dom["bytes_per_launch"] * dom["launches"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
     kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
                    "share": round(v["ms"] / total_ms, 4) if total_ms > 0 else 0.0,
@@ -261,6 +265,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": dom["bytes_per_launch"], "launches": dom["launches"],
+                         "dominant_kernel_by_time": by_time,
                          "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},
             "kernels": kernels,
             "final_cost": recs[-1]["cost"]}

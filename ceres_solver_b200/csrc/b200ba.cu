@@ -28,6 +28,7 @@
 #include "../../include/b200ba.h"
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
+#include "kernels_v2b.cuh"
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
 
@@ -113,6 +114,30 @@ bool load_nccl() {
 }
 #endif
 
+// Host vector in page-locked memory (the host-buffer LM loop mirrors what an adapter with pinned buffers does).
+struct PinnedVec {
+  double* p = nullptr;
+  size_t n = 0;
+  PinnedVec() = default;
+  PinnedVec(const PinnedVec&) = delete;
+  ~PinnedVec() { if (p != nullptr) cudaFreeHost(p); }
+  void resize(size_t m) {
+    if (m == n) return;
+    if (p != nullptr) cudaFreeHost(p);
+    p = nullptr;
+    n = m;
+    if (m > 0 && cudaMallocHost(reinterpret_cast<void**>(&p), m * sizeof(double)) != cudaSuccess) { p = nullptr; n = 0; }
+  }
+  void assign(size_t m, double v) { resize(m); for (size_t i = 0; i < n; ++i) p[i] = v; }
+  void assign(const double* b, const double* e) { resize(static_cast<size_t>(e - b)); std::memcpy(p, b, n * sizeof(double)); }
+  PinnedVec& operator=(const PinnedVec& o) { resize(o.n); if (n) std::memcpy(p, o.p, n * sizeof(double)); return *this; }
+  double* data() { return p; }
+  double* begin() { return p; }
+  double* end() { return p + n; }
+  double& operator[](size_t i) { return p[i]; }
+  size_t size() const { return n; }
+};
+
 struct EventPair {
   cudaEvent_t a, b;
   int kernel;
@@ -123,6 +148,8 @@ struct EventPair {
 struct b200_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // side stream for the big-point kernel inside the PCG
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool own_stream = false;
   int sm_count = 148;
   int C = 0, P = 0, N = 0, num_tiles = 0;
@@ -171,9 +198,14 @@ struct b200_handle {
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
   double* d_partials = nullptr;
   size_t v2_smem = 0;
+  bool v2b_ok = false;        // warp-tile versions of evaluate / schur_init / diag_blocks usable (narrow camera ranges)
+  V2View v2_init{}, v2_diag{}, v2_eval{};
+  size_t eval_v2_smem = 0, init_v2_smem = 0, diag_v2_smem = 0;
+  int diag_v2_replicas = 0;
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
   int cg_grid = 1;
+  PinnedVec hv[12];           // host-boundary LM loop vectors
   // launch geometry
   int grid_tile[K_COUNT];
   // stats
@@ -279,8 +311,12 @@ int tile_grid(b200_handle* h, K kernel, size_t smem) {
 }
 
 // ------------------------------------------------------------------------------------------------ device-pointer cores
+int sqnorm_dev(b200_handle* h, double* d_out);
+
+// d_sqnorm (optional): squared column norms of the Jacobian as written (after the fused scaling), for free with the
+// warp-tile kernel; the caller falls back to sqnorm_dev when *sqnorm_done comes back false.
 int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, double* d_gradient, bool want_jacobian,
-                 const double* d_scale, double* cost_out) {
+                 const double* d_scale, double* cost_out, double* d_sqnorm = nullptr, bool* sqnorm_done = nullptr) {
   EvalArgs a{};
   a.state = d_state;
   a.residuals = d_residuals;
@@ -290,17 +326,50 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
   a.fail_flag = h->d_fail;
   a.loss_type = h->loss_type;
   a.loss_a = h->loss_a;
+  if (sqnorm_done != nullptr) *sqnorm_done = false;
   CU(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
   const bool with_j = want_jacobian || d_gradient != nullptr;
-  if (d_gradient != nullptr)
-    CU(cudaMemsetAsync(d_gradient + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
+  const size_t coff = 3 * static_cast<size_t>(h->P);
+  if (d_gradient != nullptr) CU(cudaMemsetAsync(d_gradient + coff, 0, sizeof(double) * 9 * h->C, h->stream));
   const size_t smem = tile_smem_bytes<3, 1>();
-  if (with_j) {
+  int num_partials = h->num_tiles;
+  if (with_j && h->v2b_ok) {
+    EvalV2Args e{};
+    e.state = d_state;
+    e.residuals = d_residuals;
+    e.gradient = d_gradient;
+    e.sqnorm = d_sqnorm;
+    e.cost_partial = h->d_tile_partial;
+    e.scale = d_scale;
+    e.fail_flag = h->d_fail;
+    e.loss_type = h->loss_type;
+    e.loss_a = h->loss_a;
+    if (d_sqnorm != nullptr) CU(cudaMemsetAsync(d_sqnorm + coff, 0, sizeof(double) * 9 * h->C, h->stream));
+    OK(launch(h, K_EVAL_JAC, [&] {
+      evaluate_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->eval_v2_smem, h->stream>>>(h->v2_eval, e);
+    }));
+    num_partials = h->v2.num_ctas;
+    if (h->num_big_tiles > 0) {  // the few >32-row points: CTA-tile kernels on their tiles only
+      a.cost_partial = h->d_tile_partial + num_partials;
+      OK(launch(h, K_EVAL_JAC, [&] {
+        evaluate_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 2), kTile, smem, h->stream>>>(h->view_big, a);
+      }));
+      num_partials += h->num_big_tiles;
+      if (d_sqnorm != nullptr)
+        OK(launch(h, K_SQNORM, [&] {
+          sqnorm_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, d_sqnorm);
+        }));
+    }
+    if (d_sqnorm != nullptr) {
+      OK(allreduce_sum(h, d_sqnorm + coff, 9 * static_cast<size_t>(h->C)));
+      if (sqnorm_done != nullptr) *sqnorm_done = true;
+    }
+  } else if (with_j) {
     OK(launch(h, K_EVAL_JAC, [&] { evaluate_kernel<true><<<h->grid_tile[K_EVAL_JAC], kTile, smem, h->stream>>>(h->view, a); }));
   } else {
     OK(launch(h, K_EVAL_COST, [&] { evaluate_kernel<false><<<h->grid_tile[K_EVAL_COST], kTile, smem, h->stream>>>(h->view, a); }));
   }
-  OK(launch(h, K_MISC, [&] { sum_kernel<<<1, kVecThreads, 0, h->stream>>>(h->num_tiles, h->d_tile_partial, h->d_scalars); }));
+  OK(launch(h, K_MISC, [&] { sum_kernel<<<1, kVecThreads, 0, h->stream>>>(num_partials, h->d_tile_partial, h->d_scalars); }));
   if (d_gradient != nullptr) OK(allreduce_sum(h, d_gradient + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
   OK(allreduce_sum(h, h->d_scalars, 1));
   CU(cudaMemcpyAsync(h->h_scalars, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -343,9 +412,19 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
   st.rhs = h->d_rhs;
   st.ye = h->d_ye;
   CU(cudaMemsetAsync(h->d_rhs, 0, sizeof(double) * 9 * h->C, h->stream));
-  OK(launch(h, K_SCHUR_INIT, [&] {
-    schur_init_kernel<<<h->grid_tile[K_SCHUR_INIT], kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view, st);
-  }));
+  if (h->v2b_ok) {
+    OK(launch(h, K_SCHUR_INIT, [&] {
+      schur_init_v2_kernel<<<h->v2.num_ctas, 32 * h->v2_init.warps, h->init_v2_smem, h->stream>>>(h->v2_init, st);
+    }));
+    if (h->num_big_tiles > 0)
+      OK(launch(h, K_SCHUR_INIT, [&] {
+        schur_init_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view_big, st);
+      }));
+  } else {
+    OK(launch(h, K_SCHUR_INIT, [&] {
+      schur_init_kernel<<<h->grid_tile[K_SCHUR_INIT], kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view, st);
+    }));
+  }
   OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
   h->cur_b = d_b;
   h->cur_D = d_D;
@@ -392,7 +471,21 @@ int precond_update_dev(b200_handle* h, int type) {
   if (type == B200_PRECOND_IDENTITY) return B200_OK;
   const double* Df = h->cur_D != nullptr ? h->cur_D + 3 * static_cast<size_t>(h->P) : nullptr;
   CU(cudaMemsetAsync(h->d_upper45, 0, sizeof(double) * 45 * h->C, h->stream));
-  if (type == B200_PRECOND_SCHUR_JACOBI) {
+  if (h->v2b_ok && h->diag_v2_replicas > 0) {
+    const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
+    OK(launch(h, K_DIAG_BLOCKS, [&] {
+      if (schur)
+        diag_blocks_v2_kernel<true><<<h->v2.num_ctas, 32 * h->v2_diag.warps, h->diag_v2_smem, h->stream>>>(h->v2_diag, h->diag_v2_replicas, h->d_ete_inv, h->d_upper45);
+      else
+        diag_blocks_v2_kernel<false><<<h->v2.num_ctas, 32 * h->v2_diag.warps, h->diag_v2_smem, h->stream>>>(h->v2_diag, h->diag_v2_replicas, h->d_ete_inv, h->d_upper45);
+    }));
+    if (h->num_big_tiles > 0)
+      OK(launch(h, K_DIAG_BLOCKS, [&] {
+        const int g = std::min(h->num_big_tiles, h->sm_count);
+        if (schur) diag_blocks_kernel<true><<<g, kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view_big, h->d_ete_inv, h->d_upper45);
+        else diag_blocks_kernel<false><<<g, kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view_big, h->d_ete_inv, h->d_upper45);
+      }));
+  } else if (type == B200_PRECOND_SCHUR_JACOBI) {
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       diag_blocks_kernel<true><<<h->grid_tile[K_DIAG_BLOCKS], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->d_upper45);
     }));
@@ -403,7 +496,7 @@ int precond_update_dev(b200_handle* h, int type) {
   }
   OK(allreduce_sum(h, h->d_upper45, 45 * static_cast<size_t>(h->C)));
   return launch(h, K_INVERT9, [&] {
-    invert9_kernel<<<(h->C + 63) / 64, 64, 0, h->stream>>>(h->C, h->d_upper45, Df, h->d_blocks, h->d_minv);
+    invert9_kernel<<<(h->C + kInvWarps - 1) / kInvWarps, 32 * kInvWarps, 0, h->stream>>>(h->C, h->d_upper45, Df, h->d_blocks, h->d_minv);
   });
 }
 
@@ -448,14 +541,28 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   };
   auto product = [&](const double* vin, double* out) -> int {
     if (seeded) {
+      // The handful of >32-row points runs on a side stream, concurrently with the warp-tile kernel (both only add
+      // into the pre-seeded output with REDs); outside profiling mode, where launches are bracketed by events.
+      const bool side = h->num_big_tiles > 0 && !h->profiling;
+      if (side) {
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+        schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream2>>>(
+            h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
+        h->launches[K_SCHUR_MUL_BIG]++;
+        CU(cudaEventRecord(h->ev_join, h->stream2));
+      }
       OK(launch(h, K_SCHUR_MUL, [&] {
         schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
-      if (h->num_big_tiles > 0)
+      if (side) {
+        CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+      } else if (h->num_big_tiles > 0) {
         OK(launch(h, K_SCHUR_MUL_BIG, [&] {
           schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
               h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
         }));
+      }
       return allreduce_sum(h, out, n);
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
@@ -705,7 +812,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     }
     // Shared memory budget: `replicas` private camera vectors + per-warp {TMA ring of F cells, exchange scratch}.
     // Prefer one replica per warp (no cross-warp contention) when the camera span of a CTA is small.
-    const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 1024;
+    const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 2048;
     const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
     for (int stages = 3; stages >= 1 && v2_warps == 0; --stages) {
       const long pw = v2_per_warp_bytes(stages, kV2Scratch);
@@ -749,6 +856,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
   }
+  CU(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   if (h->world > 1) {
 #ifdef B200_WITH_NCCL
     if (desc->nccl_unique_id == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "world_size > 1 needs nccl_unique_id");
@@ -773,7 +883,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   OK(dev_alloc(&h->d_state, h->np));
   OK(dev_alloc(&h->d_residuals, 2 * n));
   OK(dev_alloc(&h->d_gradient, h->np));
-  OK(dev_alloc(&h->d_tile_partial, tiles.size()));
+  OK(dev_alloc(&h->d_tile_partial, tiles.size() + num_ctas_v2 + big_tiles.size() + 8));
   OK(dev_alloc(&h->d_fail, 4));
   OK(dev_alloc(&h->d_scalars, 64));
   OK(dev_alloc(&h->d_partial, kRedBlocks * 4));
@@ -864,9 +974,48 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     h->v2.per_warp_bytes = v2_per_warp_bytes(v2_stages, kV2Scratch);
     h->v2_smem = v2_sy_bytes(max_cam_span, v2_replicas) + static_cast<size_t>(v2_warps) * h->v2.per_warp_bytes;
     // function attributes are process-wide: always raise them to the device limit, never to this handle's need
-    CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin)));
-    CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin)));
+    CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+    CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     h->v2_ok = true;
+    if (h->v2.direct && getenv("B200_DISABLE_V2B") == nullptr) {
+      const size_t lim = prop.sharedMemPerBlockOptin - 2048;
+      // Each kernel gets as many replicas of its private accumulators as fit next to its per-warp buffers
+      // (one per warp at best), and a shallower TMA ring if even a single replica would not fit.
+      const size_t sy1 = v2_sy_bytes(max_cam_span, 1);
+      auto fit = [&](size_t per_warp, size_t acc1, int* replicas) -> size_t {
+        const size_t fixed = per_warp * v2_warps;
+        if (fixed + acc1 > lim) return lim + 1;
+        *replicas = static_cast<int>(std::min<size_t>(v2_warps, (lim - fixed) / acc1));
+        return fixed + acc1 * *replicas;
+      };
+      // evaluate: two accumulators (gradient, column norms) + per-warp staging
+      h->v2_eval = h->v2;
+      h->eval_v2_smem = fit(eval_v2_per_warp_bytes(), 2 * sy1, &h->v2_eval.replicas);
+      // schur_init: same ring as S*x with a 9-double exchange scratch
+      h->v2_init = h->v2;
+      h->init_v2_smem = lim + 1;
+      for (int st = v2_stages; st >= 1 && h->init_v2_smem > lim; --st) {
+        h->v2_init.stages = st;
+        h->v2_init.per_warp_bytes = v2_per_warp_bytes(st, kInitScratch);
+        h->init_v2_smem = fit(h->v2_init.per_warp_bytes, sy1, &h->v2_init.replicas);
+      }
+      // diag blocks: 45 doubles per camera
+      h->v2_diag = h->v2;
+      h->diag_v2_smem = lim + 1;
+      h->diag_v2_replicas = 0;
+      for (int st = v2_stages; st >= 1 && h->diag_v2_smem > lim; --st) {
+        h->v2_diag.stages = st;
+        h->diag_v2_smem = fit(diag_v2_per_warp_bytes(st), diag_v2_acc_stride(max_cam_span) * 8, &h->diag_v2_replicas);
+      }
+      if (h->diag_v2_smem > lim) h->diag_v2_replicas = 0;  // falls back to the CTA-tile kernel
+      if (h->eval_v2_smem <= lim && h->init_v2_smem <= lim) {
+        CU(cudaFuncSetAttribute(evaluate_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_init_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(diag_blocks_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(diag_blocks_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        h->v2b_ok = true;
+      }
+    }
   }
 
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
@@ -931,6 +1080,9 @@ void b200_destroy(b200_handle* h) {
     cudaEventDestroy(ep.b);
   }
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->stream2 != nullptr) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->own_stream && h->stream != nullptr) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1147,7 +1299,9 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
   const size_t nr = 2 * static_cast<size_t>(h->N);
   const size_t off = 3 * static_cast<size_t>(h->P);
   // host mirrors (host_boundary only)
-  std::vector<double> x, cand, residuals, gradient, step, delta, scaling, diagonal, lmD, model_res, sol, best;
+  // page-locked host mirrors, allocated once per handle (cudaMallocHost is far too slow to sit inside a solve)
+  PinnedVec &x = h->hv[0], &cand = h->hv[1], &residuals = h->hv[2], &gradient = h->hv[3], &step = h->hv[4], &delta = h->hv[5],
+            &scaling = h->hv[6], &diagonal = h->hv[7], &lmD = h->hv[8], &model_res = h->hv[9], &sol = h->hv[10], &best = h->hv[11];
   if (host_boundary) {
     x.assign(state_inout, state_inout + np);
     cand.resize(np); residuals.resize(nr); gradient.resize(np); step.resize(np); delta.resize(np);
@@ -1166,6 +1320,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
   b200_lm_iteration it{};
   int iteration = 0;
   bool have_scaling = false;
+  bool sqnorm_fresh = false;  // d_sqnorm holds the squared column norms of the current device Jacobian
   const int vgrid = std::min(kRedBlocks, flat_grid(h, np, 256));
 
   auto evaluate_gradient_and_jacobian = [&]() -> int {
@@ -1190,12 +1345,16 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     }
     // device-resident: scaling is fused into the Jacobian write once it is known
     const bool fuse = opt->jacobi_scaling && have_scaling;
-    OK(evaluate_dev(h, h->d_state, h->d_residuals, h->d_gradient, true, fuse ? h->d_scale : nullptr, &x_cost));
+    OK(evaluate_dev(h, h->d_state, h->d_residuals, h->d_gradient, true, fuse ? h->d_scale : nullptr, &x_cost, h->d_sqnorm,
+                    &sqnorm_fresh));
     it.cost = x_cost;
     if (opt->jacobi_scaling && !have_scaling) {
-      OK(sqnorm_dev(h, h->d_sqnorm));
+      if (!sqnorm_fresh) OK(sqnorm_dev(h, h->d_sqnorm));
+      // scale = 1/(1+sqrt(colnorm^2)); J <- J diag(scale); and colnorm^2 of the scaled J is colnorm^2 * scale^2
       OK(launch(h, K_LM_VEC, [&] { jacobi_scale_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, h->d_sqnorm, h->d_scale); }));
       OK(scale_dev(h, h->d_scale));
+      OK(launch(h, K_LM_VEC, [&] { rescale_sq_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, h->d_scale, h->d_sqnorm); }));
+      sqnorm_fresh = true;
       have_scaling = true;
     }
     double gn[2];
@@ -1253,7 +1412,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
           for (int i = 0; i < np; ++i) step[i] = -sol[i];
       }
     } else {
-      if (!reuse_diagonal) OK(sqnorm_dev(h, h->d_sqnorm));
+      if (!reuse_diagonal && !sqnorm_fresh) OK(sqnorm_dev(h, h->d_sqnorm));
       OK(launch(h, K_LM_VEC, [&] {
         lm_diagonal_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, reuse_diagonal ? 0 : 1, h->d_sqnorm, h->d_diagonal, h->d_lmD,
                                                                           opt->min_lm_diagonal, opt->max_lm_diagonal, radius);

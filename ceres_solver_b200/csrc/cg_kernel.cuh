@@ -1,16 +1,18 @@
 // One cooperative kernel per PCG iteration carries everything that is not the S*p product:
-//   phase A  q = D_f^2 p + (fixed-order sum of the per-CTA partial vectors of schur_mul_v2) [+ big-point RED buffer],
-//            partial p.q
+//   phase A  partial p.q                               (q = S*p was assembled by the product kernels)
 //   ---- grid sync ----
 //   phase B  alpha = rho / p.q ; x += alpha p ; r -= alpha q ; z = M^-1 r (9x9 block per camera) ;
 //            partial x.(b+r), r.r, r.z
 //   ---- grid sync ----
 //   phase C  the reference's termination tests (conjugate_gradients_solver.h:245-299) evaluated identically by
-//            every CTA from the same partials, beta = rho_new / rho, p = z + beta p ; CTA 0 publishes the state.
+//            every CTA from the same partials, beta = rho_new / rho, p = z + beta p, and the seed D_f^2 p of the next
+//            product ; CTA 0 publishes the state.
 // CTAs own whole cameras (28 cameras = 252 entries per 256-thread CTA), so the block-diagonal preconditioner
 // needs only the CTA's own slice of r.  All dot products are reduced in a fixed order: the PCG is deterministic
-// given q.  Replaces the reference's ~12 Eigen expressions + 3 host-synchronising dots per iteration
-// (conjugate_gradients_solver.h:162-299; cuda_vector.cc:97-181 in its CUDA variant).
+// given q.  The kernel is latency-bound (a few KB per CTA), so every operand that does not depend on a grid-wide
+// result is loaded before the grid sync that precedes its use, and each thread keeps its entry of x, r, p, z in
+// registers across the phases.  Replaces the reference's ~12 Eigen expressions + 3 host-synchronising dots per
+// iteration (conjugate_gradients_solver.h:162-299; cuda_vector.cc:97-181 in its CUDA variant).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -28,42 +30,61 @@ struct CgVecArgs {
   CgParams prm;
   int mode;
   int C;
-  // phase A inputs
   double* seed_target;         // non-null: this launch also writes the seed of the NEXT product there,
                                // seed_target = Df^2 * (p_new, or x_new in CG_RESET_FIRST)  (0 if Df is null)
   const double* Df;
-  // preconditioner
   int precond;                 // 0 identity, 1 block-diagonal inverse blocks
   const double* minv;
-  // vectors
   const double* rhs;
-  double *x, *r, *z, *p, *q;   // q doubles as the S*x_new buffer in CG_RESET_SECOND
+  double *x, *r, *z, *p, *q;   // q holds S*p (S*x_new in CG_RESET_SECOND)
   double* red;                 // [gridDim.x][4] partial sums
   CgState* st;
 };
 
-__device__ __forceinline__ double cg_block_sum(double v, double* scratch) {
-  return block_sum<kCgThreads>(v, scratch);
-}
-
-// Fixed-order sum of slot `slot` over all CTAs' partials; result broadcast to the whole CTA.
-__device__ __forceinline__ double cg_total(const double* red, int nb, int slot, double* s_bcast) {
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double acc = 0.0;
-    for (int b = threadIdx.x; b < nb; b += 32) acc += red[b * 4 + slot];
+// Sums up to three values over the CTA with one barrier pair; results valid in every thread.
+__device__ __forceinline__ void cg_block_sum3(double& a, double& b, double& c, double (*scratch)[3]) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (threadIdx.x == 0) *s_bcast = acc;
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) {
+    scratch[warp][0] = a;
+    scratch[warp][1] = b;
+    scratch[warp][2] = c;
   }
   __syncthreads();
-  return *s_bcast;
+  a = b = c = 0.0;
+#pragma unroll
+  for (int w = 0; w < kCgThreads / 32; ++w) {
+    a += scratch[w][0];
+    b += scratch[w][1];
+    c += scratch[w][2];
+  }
+}
+
+// Fixed-order totals of slots [slot0, slot0 + count) over all CTAs' partials; every thread gets them.
+__device__ __forceinline__ void cg_totals(const double* red, int nb, int slot0, int count, double* out, double* s_tot) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (warp < count) {
+    double acc = 0.0;
+    for (int b = lane; b < nb; b += 32) acc += __ldcg(red + b * 4 + slot0 + warp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_tot[warp] = acc;
+  }
+  __syncthreads();
+  for (int k = 0; k < count; ++k) out[k] = s_tot[k];
 }
 
 __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ double scratch[32];
-  __shared__ double s_bcast;
+  __shared__ double scratch[kCgThreads / 32][3];
+  __shared__ double s_tot[4];
   __shared__ double s_r[kCgCamsPerCta * 9];
   CgState* st = a.st;
   const int mode = a.mode;
@@ -76,18 +97,44 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   const int n = a.prm.n;
   const int nblocks = (a.C + kCgCamsPerCta - 1) / kCgCamsPerCta;
   const bool lane_ok = tid < kCgCamsPerCta * 9;
-  // ------------------------------------------------------------------ phase A
-  if (mode != CG_BEGIN) {
-    double acc = 0.0;
-    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-      const int j = blk * kCgCamsPerCta * 9 + tid;
-      if (lane_ok && j < n) {
-        const double* src = (mode == CG_RESET_SECOND) ? a.x : a.p;   // vector the product was taken of
-        const double qj = a.q[j];
-        acc += src[j] * qj;
+  const bool writer = (blockIdx.x == 0 && tid == 0);
+  // Fast path: one camera block per CTA (grid == nblocks) — entries stay in registers across the phases.
+  const bool single = (gridDim.x >= nblocks);
+  const int j0 = blockIdx.x * kCgCamsPerCta * 9 + tid;
+  const bool ok0 = single && lane_ok && j0 < n && blockIdx.x < nblocks;
+
+  // operands that do not depend on grid-wide results: fetch them now
+  double pj = 0.0, qj = 0.0, xj = 0.0, rj = 0.0, bj = 0.0, dj = 0.0;
+  double mrow[9];
+  if (ok0) {
+    bj = a.rhs[j0];
+    if (mode != CG_BEGIN) {
+      pj = a.p[j0];
+      qj = a.q[j0];
+      xj = a.x[j0];
+      if (mode != CG_RESET_SECOND) rj = a.r[j0];
+    }
+    if (a.Df != nullptr) dj = a.Df[j0];
+    if (a.precond != 0 && mode != CG_RESET_FIRST) {
+      const int cl = tid / 9, row = tid - 9 * cl;
+      const double* m = a.minv + 81 * static_cast<size_t>(blockIdx.x * kCgCamsPerCta + cl) + 9 * row;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) mrow[k] = m[k];
+    }
+  }
+
+  // ------------------------------------------------------------------ phase A: p.q
+  if (mode == CG_NORMAL || mode == CG_RESET_FIRST) {
+    double acc = 0.0, d1 = 0.0, d2 = 0.0;
+    if (single) {
+      acc = pj * qj;
+    } else {
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int j = blk * kCgCamsPerCta * 9 + tid;
+        if (lane_ok && j < n) acc += a.p[j] * a.q[j];
       }
     }
-    acc = cg_block_sum(acc, scratch);
+    cg_block_sum3(acc, d1, d2, scratch);
     if (tid == 0) a.red[blockIdx.x * 4 + 0] = acc;
     grid.sync();
   }
@@ -95,7 +142,8 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   // ------------------------------------------------------------------ phase B
   double alpha = 0.0;
   if (mode == CG_NORMAL || mode == CG_RESET_FIRST) {
-    const double pq = cg_total(a.red, gridDim.x, 0, &s_bcast);
+    double pq;
+    cg_totals(a.red, gridDim.x, 0, 1, &pq, s_tot);
     bool stop = false;
     int term = 0, reason = 0;
     if (!(pq > 0.0) || isinf(pq)) {
@@ -111,7 +159,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       }
     }
     if (stop) {
-      if (blockIdx.x == 0 && tid == 0) {
+      if (writer) {
         st->pq = pq;
         st->done = 1;
         st->termination = term;
@@ -121,49 +169,60 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       return;  // every CTA takes this branch together
     }
   }
+  double zj = 0.0;
   {
     double accQ = 0.0, accR = 0.0, accRho = 0.0;
     for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
       const int j = blk * kCgCamsPerCta * 9 + tid;
       const bool ok = lane_ok && j < n;
-      double rj = 0.0;
+      if (ok && !single) {  // generic path: operands from memory
+        bj = a.rhs[j];
+        if (mode != CG_BEGIN) {
+          pj = a.p[j];
+          qj = a.q[j];
+          xj = a.x[j];
+          if (mode != CG_RESET_SECOND) rj = a.r[j];
+        }
+        dj = a.Df != nullptr ? a.Df[j] : 0.0;
+      }
       if (ok) {
-        double xj;
         if (mode == CG_BEGIN) {
           xj = 0.0;
-          rj = a.rhs[j];
+          rj = bj;
           a.x[j] = 0.0;
         } else if (mode == CG_RESET_SECOND) {
-          xj = a.x[j];
-          rj = a.rhs[j] - a.q[j];           // r = b - S x   (q holds S x here)
+          rj = bj - qj;                       // r = b - S x   (q holds S x here)
         } else {
-          xj = a.x[j] + alpha * a.p[j];
+          xj += alpha * pj;
           a.x[j] = xj;
-          rj = a.r[j] - alpha * a.q[j];
-          if (mode == CG_RESET_FIRST && a.seed_target != nullptr)
-            a.seed_target[j] = a.Df != nullptr ? a.Df[j] * a.Df[j] * xj : 0.0;
+          rj -= alpha * qj;
+          if (mode == CG_RESET_FIRST && a.seed_target != nullptr) a.seed_target[j] = dj * dj * xj;
         }
         if (mode != CG_RESET_FIRST) {
           a.r[j] = rj;
-          accQ += xj * (a.rhs[j] + rj);
+          accQ += xj * (bj + rj);
           accR += rj * rj;
         }
       }
       if (mode != CG_RESET_FIRST) {
         __syncthreads();
-        if (lane_ok) s_r[tid] = rj;
+        if (lane_ok) s_r[tid] = ok ? rj : 0.0;
         __syncthreads();
         if (ok) {
-          double zj;
           if (a.precond == 0) {
             zj = rj;
           } else {
-            const int cl = tid / 9, row = tid - 9 * cl;
-            const double* m = a.minv + 81 * static_cast<size_t>(blk * kCgCamsPerCta + cl) + 9 * row;
+            const int cl = tid / 9;
             const double* rc = s_r + 9 * cl;
+            if (!single) {
+              const int row = tid - 9 * cl;
+              const double* m = a.minv + 81 * static_cast<size_t>(blk * kCgCamsPerCta + cl) + 9 * row;
+#pragma unroll
+              for (int k = 0; k < 9; ++k) mrow[k] = m[k];
+            }
             zj = 0.0;
 #pragma unroll
-            for (int k = 0; k < 9; ++k) zj += m[k] * rc[k];
+            for (int k = 0; k < 9; ++k) zj += mrow[k] * rc[k];
           }
           a.z[j] = zj;
           accRho += rj * zj;
@@ -171,15 +230,13 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       }
     }
     if (mode == CG_RESET_FIRST) {
-      if (blockIdx.x == 0 && tid == 0) {
+      if (writer) {
         st->alpha = alpha;
         st->iteration = it;   // iteration `it` is half done; the second half reads it back
       }
       return;
     }
-    accQ = cg_block_sum(accQ, scratch);
-    accR = cg_block_sum(accR, scratch);
-    accRho = cg_block_sum(accRho, scratch);
+    cg_block_sum3(accQ, accR, accRho, scratch);
     if (tid == 0) {
       a.red[blockIdx.x * 4 + 1] = accQ;
       a.red[blockIdx.x * 4 + 2] = accR;
@@ -189,10 +246,9 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   grid.sync();
 
   // ------------------------------------------------------------------ phase C
-  const double dotQ = cg_total(a.red, gridDim.x, 1, &s_bcast);
-  const double sqR = cg_total(a.red, gridDim.x, 2, &s_bcast);
-  const double rho_new = cg_total(a.red, gridDim.x, 3, &s_bcast);
-  const bool writer = (blockIdx.x == 0 && tid == 0);
+  double tot[3];
+  cg_totals(a.red, gridDim.x, 1, 3, tot, s_tot);
+  const double dotQ = tot[0], sqR = tot[1], rho_new = tot[2];
   const double norm_r = sqrt(sqR);
   double Q0_next = 0.0;
   if (mode == CG_BEGIN) {
@@ -260,12 +316,20 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       return;
     }
   }
-  for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-    const int j = blk * kCgCamsPerCta * 9 + tid;
-    if (lane_ok && j < n) {
-      const double pj = (it == 0) ? a.z[j] : a.z[j] + beta * a.p[j];
-      a.p[j] = pj;
-      if (a.seed_target != nullptr) a.seed_target[j] = a.Df != nullptr ? a.Df[j] * a.Df[j] * pj : 0.0;
+  if (single) {
+    if (ok0) {
+      const double pn = (it == 0) ? zj : zj + beta * pj;
+      a.p[j0] = pn;
+      if (a.seed_target != nullptr) a.seed_target[j0] = dj * dj * pn;
+    }
+  } else {
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+      const int j = blk * kCgCamsPerCta * 9 + tid;
+      if (lane_ok && j < n) {
+        const double pn = (it == 0) ? a.z[j] : a.z[j] + beta * a.p[j];
+        a.p[j] = pn;
+        if (a.seed_target != nullptr) a.seed_target[j] = a.Df != nullptr ? a.Df[j] * a.Df[j] * pn : 0.0;
+      }
     }
   }
   if (writer) {

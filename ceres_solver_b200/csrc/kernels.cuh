@@ -883,6 +883,7 @@ __global__ void __launch_bounds__(kTile)
           if (j != tid && s.sCam[j] == cam) {
             const double* ej = s.sE + j * 6;
             const double* fj = s.sF + j * 18;
+#pragma unroll
             for (int k = 0; k < 9; ++k) {
               B[k] += ej[0] * fj[k] + ej[3] * fj[9 + k];
               B[9 + k] += ej[1] * fj[k] + ej[4] * fj[9 + k];
@@ -916,53 +917,67 @@ __global__ void __launch_bounds__(kTile)
   }
 }
 
-// One thread per camera: M = sym(upper45) + D_c^2;  inverse by Cholesky solve against I
-// (block_random_access_diagonal_matrix.cc:90-100 / AddDiagonalAndInvert).  blocks/inverse: [81C], either may be null.
-__global__ void __launch_bounds__(64) invert9_kernel(int C, const double* __restrict__ upper45,
-                                                     const double* __restrict__ Df, double* blocks, double* inverse) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per camera: M = sym(upper45) + D_c^2; inverse by Cholesky solve against I, as the reference does with
+// selfadjointView<Upper>().llt().solve(I) (block_random_access_diagonal_matrix.cc:90-100 / AddDiagonalAndInvert).
+// blocks / inverse: [81C], either may be null.  The factor lives in shared memory; lanes 0..8 each solve one column.
+constexpr int kInvWarps = 4;
+__global__ void __launch_bounds__(32 * kInvWarps) invert9_kernel(int C, const double* __restrict__ upper45,
+                                                                 const double* __restrict__ Df, double* blocks,
+                                                                 double* inverse) {
+  __shared__ double sM[kInvWarps][81];
+  __shared__ double sL[kInvWarps][81];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * kInvWarps + warp;
   if (c >= C) return;
-  double M[81];
+  double* M = sM[warp];
+  double* L = sL[warp];
   const double* u = upper45 + 45 * static_cast<size_t>(c);
-  int idx = 0;
-  for (int a = 0; a < 9; ++a)
-    for (int b = a; b < 9; ++b) {
-      M[a * 9 + b] = u[idx];
-      M[b * 9 + a] = u[idx];
-      ++idx;
-    }
-  if (Df != nullptr)
-    for (int a = 0; a < 9; ++a) M[a * 9 + a] += Df[9 * static_cast<size_t>(c) + a] * Df[9 * static_cast<size_t>(c) + a];
-  if (blocks != nullptr)
-    for (int k = 0; k < 81; ++k) blocks[81 * static_cast<size_t>(c) + k] = M[k];
-  if (inverse == nullptr) return;
-  double L[81];
-  for (int j = 0; j < 9; ++j) {
-    double dsum = M[j * 9 + j];
-    for (int k = 0; k < j; ++k) dsum -= L[j * 9 + k] * L[j * 9 + k];
-    const double ljj = sqrt(dsum);
-    L[j * 9 + j] = ljj;
-    for (int i = j + 1; i < 9; ++i) {
-      double sv = M[j * 9 + i];
-      for (int k = 0; k < j; ++k) sv -= L[i * 9 + k] * L[j * 9 + k];
-      L[i * 9 + j] = sv / ljj;
-    }
+  for (int e = lane; e < 81; e += 32) {
+    const int a = e / 9, b = e - 9 * a;
+    const int lo = a < b ? a : b, hi = a < b ? b : a;
+    double v = u[lo * 9 - lo * (lo - 1) / 2 + (hi - lo)];
+    if (a == b && Df != nullptr) v += Df[9 * static_cast<size_t>(c) + a] * Df[9 * static_cast<size_t>(c) + a];
+    M[e] = v;
+    L[e] = 0.0;
+    if (blocks != nullptr) blocks[81 * static_cast<size_t>(c) + e] = v;
   }
-  double* inv = inverse + 81 * static_cast<size_t>(c);
-  for (int col = 0; col < 9; ++col) {
-    double yv[9];
+  __syncwarp();
+  if (inverse == nullptr) return;
+  for (int j = 0; j < 9; ++j) {
+    if (lane == 0) {
+      double d = M[j * 9 + j];
+      for (int k = 0; k < j; ++k) d -= L[j * 9 + k] * L[j * 9 + k];
+      L[j * 9 + j] = sqrt(d);
+    }
+    __syncwarp();
+    if (lane > j && lane < 9) {
+      double sv = M[j * 9 + lane];
+      for (int k = 0; k < j; ++k) sv -= L[lane * 9 + k] * L[j * 9 + k];
+      L[lane * 9 + j] = sv / L[j * 9 + j];
+    }
+    __syncwarp();
+  }
+  if (lane < 9) {
+    double yv[9], xv[9];
+#pragma unroll
     for (int i = 0; i < 9; ++i) {
-      double sv = (i == col) ? 1.0 : 0.0;
-      for (int k = 0; k < i; ++k) sv -= L[i * 9 + k] * yv[k];
+      double sv = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (k < i) sv -= L[i * 9 + k] * yv[k];
       yv[i] = sv / L[i * 9 + i];
     }
-    double xv[9];
+#pragma unroll
     for (int i = 8; i >= 0; --i) {
       double sv = yv[i];
-      for (int k = i + 1; k < 9; ++k) sv -= L[k * 9 + i] * xv[k];
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (k > i) sv -= L[k * 9 + i] * xv[k];
       xv[i] = sv / L[i * 9 + i];
     }
-    for (int i = 0; i < 9; ++i) inv[i * 9 + col] = xv[i];
+    double* inv = inverse + 81 * static_cast<size_t>(c);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) inv[i * 9 + lane] = xv[i];
   }
 }
 

@@ -144,20 +144,21 @@ __device__ __forceinline__ void cam_accumulate9(double* sy_rep, int cam_local, b
   const int lane = threadIdx.x & 31;
   const int key = active ? cam_local : (0x40000000 | lane);
   const unsigned m = __match_any_sync(0xffffffffu, key);
-  const int rank = __popc(m & ((1u << lane) - 1u));
-  const int n = __popc(m);
-  const int nmax = __reduce_max_sync(0xffffffffu, n);
-  for (int stride = 1; stride < nmax; stride <<= 1) {
-    const int src_rank = rank + stride;
-    const bool pull = ((rank & (2 * stride - 1)) == 0) && (src_rank < n);
-    const int src = pull ? static_cast<int>(__fns(m, 0, src_rank + 1)) : lane;
+  // Linked list of the lanes that share my camera (ascending lane order); pointer jumping turns it into a suffix
+  // sum in ceil(log2(group size)) rounds, after which the first lane of every group holds the group total.
+  const unsigned above = (lane == 31) ? 0u : (m & (0xfffffffeu << lane));
+  int nxt = above ? (__ffs(above) - 1) : -1;
+  while (__any_sync(0xffffffffu, nxt >= 0)) {
+    const int src = nxt >= 0 ? nxt : lane;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
       const double v = __shfl_sync(0xffffffffu, g[k], src);
-      if (pull) g[k] += v;
+      g[k] += (nxt >= 0) ? v : 0.0;
     }
+    nxt = __shfl_sync(0xffffffffu, nxt, src);
+    nxt = (src == lane) ? -1 : nxt;
   }
-  if (active && rank == 0) {
+  if (active && (m & ((1u << lane) - 1u)) == 0u) {  // first lane of its group
     double* yc = sy_rep + 9 * cam_local;
 #pragma unroll
     for (int k = 0; k < 9; ++k) atomicAdd(yc + k, g[k]);

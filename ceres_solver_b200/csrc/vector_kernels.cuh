@@ -238,6 +238,11 @@ __global__ void __launch_bounds__(256) jacobi_scale_kernel(int n, const double* 
   const int stride = gridDim.x * blockDim.x;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) scale[i] = 1.0 / (1.0 + sqrt(sqnorm[i]));
 }
+// sq <- sq * scale^2 : squared column norms after J <- J diag(scale)
+__global__ void __launch_bounds__(256) rescale_sq_kernel(int n, const double* __restrict__ scale, double* sq) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) sq[i] *= scale[i] * scale[i];
+}
 // diagonal = clamp(colnorm^2, min, max) (if refresh) ; D = sqrt(diagonal / radius)   levenberg_marquardt_strategy.cc:79-95
 __global__ void __launch_bounds__(256) lm_diagonal_kernel(int n, int refresh, const double* __restrict__ sqnorm,
                                                           double* diagonal, double* D, double min_d, double max_d,
