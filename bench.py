@@ -28,6 +28,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
+NCU_TRAFFIC = {("ladybug-1723", "schur_multiply"): 141.14e6 + 3.62e6, ("venice-1778", "schur_multiply"): 1030.5e6 + 3.9e6}
+
 METRIC = "lm_iterations_per_sec"
 UNIT = "LM iterations/s"
 
@@ -263,7 +266,7 @@ def main():
                     "d2h_bytes_per_step": d2h // e2e_iters, "device_seconds": e2e_dev_s, "wall_seconds": e2e_wall_s},
             "gpu_launches": launches, "clocks": clocks, "wall_seconds": wall_s,
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((workload, dom_name)), "peak_source": peak_src,
                          "bytes_per_launch": dom["bytes_per_launch"], "launches": dom["launches"],
                          "dominant_kernel_by_time": by_time,
                          "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},

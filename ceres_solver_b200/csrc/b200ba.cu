@@ -199,7 +199,9 @@ struct b200_handle {
   double* d_partials = nullptr;
   size_t v2_smem = 0;
   bool v2b_ok = false;        // warp-tile versions of evaluate / schur_init / diag_blocks usable (narrow camera ranges)
-  V2View v2_init{}, v2_diag{}, v2_eval{};
+  V2View v2_init{}, v2_diag{}, v2_eval{}, v2_mul{};
+  size_t mul_smem = 0;
+  bool mul_v3 = false;
   size_t eval_v2_smem = 0, init_v2_smem = 0, diag_v2_smem = 0;
   int diag_v2_replicas = 0;
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
@@ -444,7 +446,8 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
       }));
     OK(launch(h, K_SCHUR_MUL, [&] {
-      schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
+      if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
     }));
     if (!h->v2.direct)
       OK(launch(h, K_CAM_REDUCE, [&] {
@@ -553,7 +556,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
+        if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
       if (side) {
         CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -794,7 +798,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   }
   const int num_ctas_v2 = prop.multiProcessorCount;
   std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2);
-  int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1;
+  int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1, mul_warps = 0, mul_stages = 0, mul_replicas = 1;
   if (v2_possible && !wtiles.empty()) {
     const long T = static_cast<long>(wtiles.size());
     for (int b = 0; b < num_ctas_v2; ++b) {
@@ -814,20 +818,33 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     // Prefer one replica per warp (no cross-warp contention) when the camera span of a CTA is small.
     const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 2048;
     const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
-    for (int stages = 3; stages >= 1 && v2_warps == 0; --stages) {
-      const long pw = v2_per_warp_bytes(stages, kV2Scratch);
-      long w = (total - sy1) / pw;                       // warps with a single shared copy
-      long wr = total / (pw + sy1);                      // warps with one copy each
-      const long cap = kV2MaxThreads / 32;
-      if (wr >= cap) {                                    // everything fits with per-warp copies
-        v2_warps = static_cast<int>(cap);
-        v2_replicas = v2_warps;
-        v2_stages = stages;
-      } else if (w >= (stages >= 2 ? 8 : 4)) {
-        v2_warps = static_cast<int>(std::min(w, cap));
-        v2_stages = stages;
-        v2_replicas = static_cast<int>(std::max<long>(1, std::min<long>(v2_warps, (total - v2_warps * pw) / sy1)));
+    auto choose = [&](long cap, int max_stages, int* warps, int* stages_out, int* replicas) {
+      *warps = 0;
+      for (int stages = max_stages; stages >= 1 && *warps == 0; --stages) {
+        const long pw = v2_per_warp_bytes(stages, kV2Scratch);
+        long w = (total - sy1) / pw;                       // warps with a single shared copy
+        long wr = total / (pw + sy1);                      // warps with one copy each
+        if (wr >= cap) {                                    // everything fits with per-warp copies
+          *warps = static_cast<int>(cap);
+          *replicas = *warps;
+          *stages_out = stages;
+        } else if (w >= (stages >= 2 ? 8 : 4)) {
+          *warps = static_cast<int>(std::min(w, cap));
+          *stages_out = stages;
+          *replicas = static_cast<int>(std::max<long>(1, std::min<long>(*warps, (total - *warps * pw) / sy1)));
+        }
       }
+    };
+    choose(kV2MaxThreads / 32, 3, &v2_warps, &v2_stages, &v2_replicas);
+    // the S*x kernel runs under 128 registers: up to 16 warps, 2-deep ring
+    choose(kV3MaxThreads / 32, 2, &mul_warps, &mul_stages, &mul_replicas);
+    if (const char* e = getenv("B200_V3_WARPS")) {  // tuning knob
+      const int w = atoi(e);
+      if (w >= 1 && w <= mul_warps) { mul_warps = w; mul_replicas = std::min(mul_replicas, w); }
+    }
+    if (const char* e = getenv("B200_V3_REPLICAS")) {
+      const int r = atoi(e);
+      if (r >= 1 && r <= mul_replicas) mul_replicas = r;
     }
     if (v2_warps == 0) v2_possible = false;  // camera vector does not fit next to the tile buffers: v1 kernels
   } else {
@@ -973,6 +990,18 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     }
     h->v2.per_warp_bytes = v2_per_warp_bytes(v2_stages, kV2Scratch);
     h->v2_smem = v2_sy_bytes(max_cam_span, v2_replicas) + static_cast<size_t>(v2_warps) * h->v2.per_warp_bytes;
+    h->v2_mul = h->v2;
+    if (mul_warps > 0 && getenv("B200_MUL_V2") == nullptr) {
+      h->v2_mul.warps = mul_warps;
+      h->v2_mul.stages = mul_stages;
+      h->v2_mul.replicas = mul_replicas;
+      h->v2_mul.per_warp_bytes = v2_per_warp_bytes(mul_stages, kV2Scratch);
+      h->mul_smem = v2_sy_bytes(max_cam_span, mul_replicas) + static_cast<size_t>(mul_warps) * h->v2_mul.per_warp_bytes;
+      h->mul_v3 = true;
+      CU(cudaFuncSetAttribute(schur_mul_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+    } else {
+      h->mul_smem = h->v2_smem;
+    }
     // function attributes are process-wide: always raise them to the device limit, never to this handle's need
     CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));

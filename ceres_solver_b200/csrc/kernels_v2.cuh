@@ -301,6 +301,138 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same product, tuned for occupancy instead of per-warp latency: nothing is carried in registers from one tile to the
+// next (the E cells, row words and (E'E)^-1 of the NEXT tile are only pulled towards L2 with prefetch.global.L2, one
+// 128-byte line per lane), which brings the kernel under 128 registers so that 16 warps per SM are resident
+// (ncu on the register-pipelined variant: 162 registers -> 12 warps, issue slots 32 % busy, 47 us on Ladybug-1723).
+// ------------------------------------------------------------------------------------------------
+constexpr int kV3MaxThreads = 512;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__global__ void __launch_bounds__(kV3MaxThreads, 1)
+    schur_mul_v3_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
+                        const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sy = reinterpret_cast<double*>(smem_raw);
+  const WarpCtx c = v2_warp_ctx(v, smem_raw, kV2Scratch);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = v.cta_part[blockIdx.x];
+  const int2 cr = v.cta_cam[blockIdx.x];
+  int t_issue;
+  v2_prologue(v, sy, c, part, cr, t_issue);
+  double* my_y = sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span);
+  const char* Ebytes = reinterpret_cast<const char*>(v.p.E());
+  int it = 0;
+  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
+    const int s = it % v.stages;
+    const uint32_t parity = (it / v.stages) & 1;
+    const WarpTile wt = v.wtiles[tile];
+    if (tile + v.warps < part.y) {  // pull the next tile's non-TMA operands towards L2
+      const WarpTile nt = v.wtiles[tile + v.warps];
+      if (lane < 12) {
+        if (128 * lane < 48 * nt.row_count) prefetch_l2(Ebytes + 48 * static_cast<size_t>(nt.row_begin) + 128 * lane);
+      } else if (lane < 24) {
+        if (128 * (lane - 12) < 48 * nt.pt_count)
+          prefetch_l2(reinterpret_cast<const char*>(ete_inv + 6 * static_cast<size_t>(nt.pt_begin)) + 128 * (lane - 12));
+      } else if (lane == 24) {
+        prefetch_l2(v.row_meta + nt.row_begin);
+      }
+    }
+    const bool active = lane < wt.row_count;
+    const size_t row = static_cast<size_t>(wt.row_begin) + lane;
+    const uint32_t meta = active ? __ldg(v.row_meta + row) : 0u;
+    const int cam = static_cast<int>(meta & 0x7fffffffu);
+    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      const double2* ep = reinterpret_cast<const double2*>(v.p.E() + 6 * row);
+      e0 = __ldg(ep);
+      e1 = __ldg(ep + 1);
+      e2 = __ldg(ep + 2);
+    }
+    {
+      double xc[9];
+      if (active) {
+        const double* xcp = x + 9 * static_cast<size_t>(cam);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+      }
+      mbar_wait(c.bars + s, parity);
+      if (active) {
+        const double* fr = c.sF + s * 576 + lane * 18;
+        double ta = 0.0, tb = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // row 0 = elements 0..8, row 1 = 9..17; element 8|9 share a double2
+          const double2 a = lds2(fr + 2 * k);
+          t0 += a.x * xc[2 * k];
+          ta += a.y * xc[2 * k + 1];
+        }
+        {
+          const double2 a = lds2(fr + 8);
+          t0 += a.x * xc[8];
+          t1 += a.y * xc[0];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double2 a = lds2(fr + 10 + 2 * k);
+          t1 += a.x * xc[2 * k + 1];
+          tb += a.y * xc[2 * k + 2];
+        }
+        t0 += ta;
+        t1 += tb;
+        c.sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
+        c.sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
+        c.sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+      }
+    }
+    __syncwarp();
+    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      for (int j = sg.first; j < sg.end; ++j) {
+        u0 += c.sW[j * 3 + 0];
+        u1 += c.sW[j * 3 + 1];
+        u2 += c.sW[j * 3 + 2];
+      }
+      const double* pi = ete_inv + 6 * static_cast<size_t>(wt.pt_begin + sg.lpt);
+      const double2 pa = __ldg(reinterpret_cast<const double2*>(pi)), pb = __ldg(reinterpret_cast<const double2*>(pi) + 1),
+                    pc = __ldg(reinterpret_cast<const double2*>(pi) + 2);
+      const double v0 = -(pa.x * u0 + pa.y * u1 + pb.x * u2);
+      const double v1 = -(pa.y * u0 + pb.y * u1 + pc.x * u2);
+      const double v2 = -(pb.x * u0 + pc.x * u1 + pc.y * u2);
+      t0 += e0.x * v0 + e0.y * v1 + e1.x * v2;
+      t1 += e1.y * v0 + e2.x * v1 + e2.y * v2;
+      const double* fr = c.sF + s * 576 + lane * 18;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double2 a = lds2(fr + 2 * k);
+        g[2 * k] = a.x * t0;
+        g[2 * k + 1] = a.y * t0;
+      }
+      {
+        const double2 a = lds2(fr + 8);
+        g[8] = a.x * t0;
+        g[0] += a.y * t1;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double2 a = lds2(fr + 10 + 2 * k);
+        g[2 * k + 1] += a.x * t1;
+        g[2 * k + 2] += a.y * t1;
+      }
+    }
+    cam_accumulate9(my_y, cam - cr.x, active, g);
+    __syncwarp();
+    if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
+    t_issue += v.warps;
+  }
+  v2_epilogue(v, sy, cr, y);
+}
+
+// ------------------------------------------------------------------------------------------------
 // y = J'(J x) + D^2 x in one pass: point part written directly (owned by the tile), camera part -> partials.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kV2MaxThreads, 1)

@@ -388,6 +388,27 @@ __host__ __device__ inline size_t diag_v2_acc_stride(int max_cam_span) {
 }
 __host__ __device__ inline int diag_v2_per_warp_bytes(int stages) { return (stages * 4608 + 32 * 48 + 32 * 4 + 8 * stages + 15) & ~15; }
 
+__host__ __device__ constexpr int upper9_offset(int a) { return a * 9 - a * (a - 1) / 2; }
+
+// Rows [A0, A1) of the packed upper triangle of  F_i'F_i - W_i' (P buf)  for one Jacobian row, accumulated per camera.
+template <bool kSchur, int A0, int A1>
+__device__ __forceinline__ void diag_rows(const double (&f)[18], const double (&W)[27], const double (&PB)[27],
+                                          double* my_acc, int cam_local, bool active) {
+  constexpr int K = upper9_offset(A1) - upper9_offset(A0);
+  double mb[K];
+  int q = 0;
+#pragma unroll
+  for (int aa = A0; aa < A1; ++aa) {
+#pragma unroll
+    for (int bb = aa; bb < 9; ++bb) {
+      double mm = f[aa] * f[bb] + f[9 + aa] * f[9 + bb];
+      if (kSchur) mm -= W[aa] * PB[bb] + W[9 + aa] * PB[9 + bb] + W[18 + aa] * PB[18 + bb];
+      mb[q++] = mm;
+    }
+  }
+  cam_accumulate<K>(my_acc, cam_local, active, mb, 45, upper9_offset(A0));
+}
+
 template <bool kSchur>
 __global__ void __launch_bounds__(kV2MaxThreads, 1)
     diag_blocks_v2_kernel(V2View v, int replicas, const double* __restrict__ ete_inv, double* out45) {
@@ -488,19 +509,11 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
         PB[18 + k] = pinv[2] * B[k] + pinv[4] * B[9 + k] + pinv[5] * B[18 + k];
       }
     }
-    // 45 packed entries per row, accumulated in three chunks of 15 to bound the live registers
-#pragma unroll
-    for (int chunk = 0; chunk < 3; ++chunk) {
-      double mb[15];
-#pragma unroll
-      for (int q = 0; q < 15; ++q) {
-        const int aa = upper9_row(chunk * 15 + q), bb = upper9_col(chunk * 15 + q);
-        double mm = f[aa] * f[bb] + f[9 + aa] * f[9 + bb];
-        if (kSchur) mm -= W[aa] * PB[bb] + W[9 + aa] * PB[9 + bb] + W[18 + aa] * PB[18 + bb];
-        mb[q] = mm;
-      }
-      cam_accumulate<15>(my_acc, cam - cr.x, active, mb, 45, chunk * 15);
-    }
+    // 45 packed upper-triangle entries per row, accumulated in three groups of matrix rows ({0,1}, {2,3,4}, {5..8}:
+    // 17 + 18 + 10 entries) to bound the live registers; all indices are compile-time after unrolling.
+    diag_rows<kSchur, 0, 2>(f, W, PB, my_acc, cam - cr.x, active);
+    diag_rows<kSchur, 2, 5>(f, W, PB, my_acc, cam - cr.x, active);
+    diag_rows<kSchur, 5, 9>(f, W, PB, my_acc, cam - cr.x, active);
     __syncwarp();
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
