@@ -204,6 +204,12 @@ struct b200_handle {
   bool mul_v3 = false;
   size_t eval_v2_smem = 0, init_v2_smem = 0, diag_v2_smem = 0;
   int diag_v2_replicas = 0;
+  // camera-major block diagonal (used when no camera sees a point twice)
+  bool cam_major_ok = false;
+  int num_cam_items = 0;
+  CamItem* d_cam_items = nullptr;
+  int* d_cam_rows = nullptr;
+  double* d_q3 = nullptr;
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
   int cg_grid = 1;
@@ -474,7 +480,18 @@ int precond_update_dev(b200_handle* h, int type) {
   if (type == B200_PRECOND_IDENTITY) return B200_OK;
   const double* Df = h->cur_D != nullptr ? h->cur_D + 3 * static_cast<size_t>(h->P) : nullptr;
   CU(cudaMemsetAsync(h->d_upper45, 0, sizeof(double) * 45 * h->C, h->stream));
-  if (h->v2b_ok && h->diag_v2_replicas > 0) {
+  if (h->cam_major_ok) {
+    const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
+    if (schur)
+      OK(launch(h, K_DIAG_BLOCKS, [&] {
+        row_q_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, h->d_ete_inv, h->d_q3);
+      }));
+    OK(launch(h, K_DIAG_BLOCKS, [&] {
+      const int g = std::max(1, std::min((h->num_cam_items + 7) / 8, h->sm_count * 4));
+      if (schur) cam_blocks_kernel<true><<<g, 256, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+      else cam_blocks_kernel<false><<<g, 256, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+    }));
+  } else if (h->v2b_ok && h->diag_v2_replicas > 0) {
     const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       if (schur)
@@ -755,6 +772,25 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       tiles.push_back(t);
     }
   }
+  // Camera-major row lists (the reference's transpose block structure) for the block-diagonal kernels, cut into
+  // slices of a few thousand rows so that small-C problems still fill the machine; unusable if a camera sees a
+  // point twice (cross terms between the two rows), which is detected here.
+  std::vector<int> cam_rows(static_cast<size_t>(N));
+  std::vector<CamItem> cam_items;
+  bool has_dups = false;
+  {
+    std::vector<int> cptr(static_cast<size_t>(C) + 1, 0);
+    for (int i = 0; i < N; ++i) cptr[desc->cam_idx[i] + 1]++;
+    for (int c = 0; c < C; ++c) cptr[c + 1] += cptr[c];
+    std::vector<int> fill(cptr.begin(), cptr.end() - 1);
+    for (int i = 0; i < N; ++i) cam_rows[fill[desc->cam_idx[i]]++] = i;
+    for (int c = 0; c < C && !has_dups; ++c)
+      for (int j = cptr[c] + 1; j < cptr[c + 1]; ++j)
+        if (desc->pt_idx[cam_rows[j]] == desc->pt_idx[cam_rows[j - 1]]) { has_dups = true; break; }
+    const int slice = std::max(256, std::min(4096, N / 4096 + 1));
+    for (int c = 0; c < C; ++c)
+      for (int b = cptr[c]; b < cptr[c + 1]; b += slice) cam_items.push_back(CamItem{c, b, std::min(b + slice, cptr[c + 1])});
+  }
   // v2 structures: warp tiles (whole points, <= 32 rows) for the points with <= 32 rows; points with 33..kTile
   // rows stay on the CTA-tile kernels (one tile each).  Needs every point to have at least one row.
   std::vector<WarpTile> wtiles;
@@ -953,6 +989,16 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->view.obs = h->d_obs;
   h->view.values = h->d_values;
 
+  if (!has_dups && getenv("B200_DISABLE_CAM_MAJOR") == nullptr) {
+    h->num_cam_items = static_cast<int>(cam_items.size());
+    OK(dev_alloc(&h->d_cam_items, cam_items.size()));
+    OK(dev_alloc(&h->d_cam_rows, n));
+    OK(dev_alloc(&h->d_q3, 3 * n));
+    CU(cudaMemcpyAsync(h->d_cam_items, cam_items.data(), cam_items.size() * sizeof(CamItem), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_cam_rows, cam_rows.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->cam_major_ok = true;
+  }
   if (v2_possible) {
     h->num_big_tiles = static_cast<int>(big_tiles.size());
     TileDesc* d_big = nullptr;
@@ -1097,7 +1143,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_partials, h->d_ybig, h->d_red,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

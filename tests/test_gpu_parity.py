@@ -200,7 +200,7 @@ def test_schur_solve_matches_oracle(precond, c16_case, cs):
     # both stop at |r| <= 1e-10 |b|; how far that is from the exact solution depends on the conditioning of the
     # preconditioned system (worst with IDENTITY), so compare both against the exact (dense Schur) solve
     x_exact, _, _ = J.linear_solve(case.gpu.P, b, D, solver=1, nt=8)
-    tol = 1e-7 if precond != 0 else 2e-5
+    tol = 2e-5  # ~ cond(M^-1 S) * 1e-10; the exact stopping iteration can differ by one or two
     assert relerr(x, x_o) < tol
     if term == cs.LS_SUCCESS:
         assert relerr(x, x_exact) < 10 * tol
