@@ -193,6 +193,8 @@ struct b200_handle {
   V2View v2{};
   ProblemView view_big{};   // CTA tiles holding only the points with more than 32 rows
   int num_big_tiles = 0;
+  bool big_folded = false;   // S*x handles them inside schur_mul_v3_kernel (no extra launch)
+  int2* d_cta_big = nullptr;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
@@ -460,7 +462,7 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         cam_reduce_kernel<<<(n + 63) / 64, 256, h->v2.num_ctas * sizeof(int2), h->stream>>>(
             n, h->v2.num_ctas, h->d_cta_cam, h->d_partials, 9 * h->v2.max_cam_span, seed, d_x, d_y, 0, done_flag);
       }));
-    if (h->num_big_tiles > 0)
+    if (h->num_big_tiles > 0 && !h->big_folded)
       OK(launch(h, K_SCHUR_MUL_BIG, [&] {
         schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
             h->view_big, h->d_ete_inv, d_x, d_y, done_flag);
@@ -563,7 +565,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     if (seeded) {
       // The handful of >32-row points runs on a side stream, concurrently with the warp-tile kernel (both only add
       // into the pre-seeded output with REDs); outside profiling mode, where launches are bracketed by events.
-      const bool side = h->num_big_tiles > 0 && !h->profiling;
+      const bool side = h->num_big_tiles > 0 && !h->profiling && !h->big_folded;
       if (side) {
         CU(cudaEventRecord(h->ev_fork, h->stream));
         CU(cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
@@ -578,7 +580,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       }));
       if (side) {
         CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-      } else if (h->num_big_tiles > 0) {
+      } else if (h->num_big_tiles > 0 && !h->big_folded) {
         OK(launch(h, K_SCHUR_MUL_BIG, [&] {
           schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
               h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
@@ -833,19 +835,34 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     }
   }
   const int num_ctas_v2 = prop.multiProcessorCount;
-  std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2);
+  std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2), cta_big(num_ctas_v2, make_int2(0, 0));
   int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1, mul_warps = 0, mul_stages = 0, mul_replicas = 1;
   if (v2_possible && !wtiles.empty()) {
-    const long T = static_cast<long>(wtiles.size());
+    // Static partition by row position: CTA b owns the warp tiles (and the >32-row points) that start inside
+    // rows [N*b/n, N*(b+1)/n), so that neighbouring CTAs stream neighbouring HBM ranges and the big points add
+    // to the balance of the CTA that takes them.
+    const int T = static_cast<int>(wtiles.size());
+    auto owner = [&](int row) { return static_cast<int>(static_cast<long>(row) * num_ctas_v2 / std::max(N, 1)); };
+    {
+      int t = 0, g = 0;
+      for (int b = 0; b < num_ctas_v2; ++b) {
+        const int t0 = t, g0 = g;
+        while (t < T && owner(wtiles[t].row_begin) <= b) ++t;
+        while (g < static_cast<int>(big_tiles.size()) && owner(big_tiles[g].obs_begin) <= b) ++g;
+        cta_part[b] = make_int2(t0, t);
+        cta_big[b] = make_int2(g0, g);
+      }
+    }
     for (int b = 0; b < num_ctas_v2; ++b) {
-      const int t0 = static_cast<int>(T * b / num_ctas_v2), t1 = static_cast<int>(T * (b + 1) / num_ctas_v2);
-      cta_part[b] = make_int2(t0, t1);
       int lo = C, hi = 0;
-      for (int t = t0; t < t1; ++t)
-        for (int r = wtiles[t].row_begin; r < wtiles[t].row_begin + wtiles[t].row_count; ++r) {
+      auto span = [&](int r0, int r1) {
+        for (int r = r0; r < r1; ++r) {
           lo = std::min(lo, desc->cam_idx[r]);
           hi = std::max(hi, desc->cam_idx[r] + 1);
         }
+      };
+      for (int t = cta_part[b].x; t < cta_part[b].y; ++t) span(wtiles[t].row_begin, wtiles[t].row_begin + wtiles[t].row_count);
+      for (int g = cta_big[b].x; g < cta_big[b].y; ++g) span(big_tiles[g].obs_begin, big_tiles[g].obs_begin + big_tiles[g].obs_count);
       if (hi <= lo) { lo = 0; hi = 0; }
       cta_cam[b] = make_int2(lo, hi);
       max_cam_span = std::max(max_cam_span, hi - lo);
@@ -1017,8 +1034,12 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaMemcpyAsync(h->d_row_meta, row_meta.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_cta_part, cta_part.data(), cta_part.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->d_cta_cam, cta_cam.data(), cta_cam.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+    OK(dev_alloc(&h->d_cta_big, cta_big.size()));
+    CU(cudaMemcpyAsync(h->d_cta_big, cta_big.data(), cta_big.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->v2.p = h->view;
+    h->v2.cta_big = h->d_cta_big;
+    h->v2.big_tiles = d_big;
     h->v2.wtiles = h->d_wtiles;
     h->v2.row_meta = h->d_row_meta;
     h->v2.cta_part = h->d_cta_part;
@@ -1044,6 +1065,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       h->v2_mul.per_warp_bytes = v2_per_warp_bytes(mul_stages, kV2Scratch);
       h->mul_smem = v2_sy_bytes(max_cam_span, mul_replicas) + static_cast<size_t>(mul_warps) * h->v2_mul.per_warp_bytes;
       h->mul_v3 = true;
+      // the S*x kernel takes the >32-row points itself when its TMA rings can stage a kTile-row point
+      h->big_folded = mul_warps >= kTile / 32 &&
+                      static_cast<size_t>(mul_warps) * h->v2_mul.per_warp_bytes >= kTile * 192 + 160 &&
+                      getenv("B200_DISABLE_BIG_FOLD") == nullptr;
       CU(cudaFuncSetAttribute(schur_mul_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     } else {
       h->mul_smem = h->v2_smem;
@@ -1143,7 +1168,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

@@ -27,6 +27,8 @@ struct V2View {
   const uint32_t* row_meta;  // [N] camera | (first row of its point ? 1u << 31 : 0)
   const int2* cta_part;      // per CTA: [tile_begin, tile_end)
   const int2* cta_cam;       // per CTA: [cam_lo, cam_hi) touched by its tiles
+  const int2* cta_big;       // per CTA: [begin, end) into big_tiles: the >32-row points inside its row range
+  const TileDesc* big_tiles; // one point each, 33..kTile rows
   double* partials;          // [num_ctas][9 * max_cam_span]
   int num_ctas;
   int max_cam_span;
@@ -306,6 +308,97 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
 // 128-byte line per lane), which brings the kernel under 128 registers so that 16 warps per SM are resident
 // (ncu on the register-pipelined variant: 162 registers -> 12 warps, issue slots 32 % busy, 47 us on Ladybug-1723).
 // ------------------------------------------------------------------------------------------------
+// The few points with 33..kTile rows that fall inside this CTA's row range: processed by the whole CTA after the
+// warp tiles (the warps' TMA rings are idle by then and provide the staging memory), one point at a time:
+// u = sum_rows E'(F x) through a CTA reduction, then the same update as the warp path, accumulated into the
+// CTA-private camera vector.  Every thread of the CTA must call this (it contains CTA barriers).
+__device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned char* ring, double* sy_rep0, int2 cr,
+                                                     const double* __restrict__ ete_inv, const double* __restrict__ x) {
+  const int2 br = v.cta_big[blockIdx.x];
+  if (br.y <= br.x) return;  // uniform per CTA
+  double* sF = reinterpret_cast<double*>(ring);
+  double* sE = sF + kTile * 18;
+  double* sU = sE + kTile * 6;                 // [4 warps][3] partial sums + [3] result
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sU + 16);
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  for (int b = br.x; b < br.y; ++b) {
+    const TileDesc d = v.big_tiles[b];
+    if (tid == 0) {
+      mbar_arrive_expect_tx(bar, d.obs_count * 192u);
+      bulk_g2s(sE, v.p.E() + 6 * static_cast<size_t>(d.obs_begin), d.obs_count * 48u, bar);
+      bulk_g2s(sF, v.p.F() + 18 * static_cast<size_t>(d.obs_begin), d.obs_count * 144u, bar);
+    }
+    const bool active = tid < d.obs_count;
+    int cam = 0;
+    double xc[9];
+    if (active) {
+      cam = static_cast<int>(__ldg(v.row_meta + d.obs_begin + tid) & 0x7fffffffu);
+      const double* xcp = x + 9 * static_cast<size_t>(cam);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    double f[18];
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(sF + tid * 18 + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        t0 += f[k] * xc[k];
+        t1 += f[9 + k] * xc[k];
+      }
+      e0 = lds2(sE + tid * 6);
+      e1 = lds2(sE + tid * 6 + 2);
+      e2 = lds2(sE + tid * 6 + 4);
+      w0 = e0.x * t0 + e1.y * t1;
+      w1 = e0.y * t0 + e2.x * t1;
+      w2 = e1.x * t0 + e2.y * t1;
+    }
+    if (tid < kTile) {  // the first four warps hold all rows
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+        w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+      }
+      if ((tid & 31) == 0) {
+        sU[(tid >> 5) * 3 + 0] = w0;
+        sU[(tid >> 5) * 3 + 1] = w1;
+        sU[(tid >> 5) * 3 + 2] = w2;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const double u0 = sU[0] + sU[3] + sU[6] + sU[9], u1 = sU[1] + sU[4] + sU[7] + sU[10], u2 = sU[2] + sU[5] + sU[8] + sU[11];
+      const double* pi = ete_inv + 6 * static_cast<size_t>(d.pt_begin);
+      const double p0 = __ldg(pi), p1 = __ldg(pi + 1), p2 = __ldg(pi + 2), p3 = __ldg(pi + 3), p4 = __ldg(pi + 4), p5 = __ldg(pi + 5);
+      const double v0 = -(p0 * u0 + p1 * u1 + p2 * u2);
+      const double v1 = -(p1 * u0 + p3 * u1 + p4 * u2);
+      const double v2 = -(p2 * u0 + p4 * u1 + p5 * u2);
+      t0 += e0.x * v0 + e0.y * v1 + e1.x * v2;
+      t1 += e1.y * v0 + e2.x * v1 + e2.y * v2;
+      double* yc = sy_rep0 + 9 * (cam - cr.x);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(yc + k, f[k] * t0 + f[9 + k] * t1);
+    }
+    __syncthreads();  // staging and sU are reused by the next point
+  }
+}
+
 constexpr int kV3MaxThreads = 512;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
@@ -429,6 +522,7 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
   }
+  schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x);
   v2_epilogue(v, sy, cr, y);
 }
 
