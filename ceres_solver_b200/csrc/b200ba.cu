@@ -195,6 +195,8 @@ struct b200_handle {
   int num_big_tiles = 0;
   bool big_folded = false;   // S*x handles them inside schur_mul_v3_kernel (no extra launch)
   int2* d_cta_big = nullptr;
+  uint32_t* d_tile_meta = nullptr;
+  bool mul_v4 = false;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
@@ -454,7 +456,8 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
       }));
     OK(launch(h, K_SCHUR_MUL, [&] {
-      if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      if (h->mul_v4) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
     }));
     if (!h->v2.direct)
@@ -575,7 +578,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        if (h->mul_v4) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
       if (side) {
@@ -1073,6 +1077,51 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     } else {
       h->mul_smem = h->v2_smem;
     }
+    // v4 (all operands through the TMA ring, x staged in shared memory): needs the narrow camera ranges of the
+    // direct-flush mode; 12 warps x 2 stages when they fit next to the private camera vector(s).
+    if (h->mul_v3 && h->v2.direct && getenv("B200_MUL_V3") == nullptr) {
+      const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 2048;
+      const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
+      int w4 = kV4MaxThreads / 32;
+      if (const char* e = getenv("B200_V4_WARPS")) w4 = std::max(4, std::min(w4, atoi(e)));
+      const int st4 = 2;
+      for (; w4 >= 8; --w4) {
+        const long rem = total - static_cast<long>(w4) * v4_per_warp_bytes(st4) - sy1 /* staged x */;
+        if (rem < sy1) continue;
+        int rep4 = static_cast<int>(std::min<long>(w4, rem / sy1));
+        if (const char* e = getenv("B200_V4_REPLICAS")) rep4 = std::max(1, std::min(rep4, atoi(e)));
+        std::vector<uint32_t> meta(static_cast<size_t>(wtiles.size()) * kV4MetaWords, 0u);
+        for (int b = 0; b < num_ctas_v2; ++b)
+          for (int t = cta_part[b].x; t < cta_part[b].y; ++t) {
+            uint32_t* m = meta.data() + static_cast<size_t>(t) * kV4MetaWords;
+            const WarpTile& wt = wtiles[t];
+            for (int r = 0; r < wt.row_count; ++r) m[r] = row_meta[wt.row_begin + r];
+            m[32] = static_cast<uint32_t>(wt.row_begin);
+            m[33] = static_cast<uint32_t>(wt.pt_begin);
+            m[34] = static_cast<uint32_t>(wt.row_count) | (static_cast<uint32_t>(wt.pt_count) << 16);
+            const int tn = t + w4 * st4;
+            if (tn < cta_part[b].y) {
+              m[36] = static_cast<uint32_t>(wtiles[tn].row_begin);
+              m[37] = static_cast<uint32_t>(wtiles[tn].pt_begin);
+              m[38] = static_cast<uint32_t>(wtiles[tn].row_count) | (static_cast<uint32_t>(wtiles[tn].pt_count) << 16);
+            }
+          }
+        OK(dev_alloc(&h->d_tile_meta, meta.size()));
+        CU(cudaMemcpyAsync(h->d_tile_meta, meta.data(), meta.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        h->v2_mul.warps = w4;
+        h->v2_mul.stages = st4;
+        h->v2_mul.replicas = rep4;
+        h->v2_mul.per_warp_bytes = v4_per_warp_bytes(st4);
+        h->v2_mul.tile_meta = h->d_tile_meta;
+        h->v2_mul.stage_x = 1;
+        h->mul_smem = v2_sy_bytes(max_cam_span, rep4) + v4_sx_bytes(max_cam_span, 1) + static_cast<size_t>(w4) * h->v2_mul.per_warp_bytes;
+        h->mul_v4 = true;
+        h->big_folded = getenv("B200_DISABLE_BIG_FOLD") == nullptr;
+        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        break;
+      }
+    }
     // function attributes are process-wide: always raise them to the device limit, never to this handle's need
     CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
@@ -1118,6 +1167,12 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     }
   }
 
+  if (getenv("B200_VERBOSE") != nullptr)
+    fprintf(stderr,
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
+            C, P, N, wtiles.size(), big_tiles.size(), max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
+            h->mul_v4 ? "v4" : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
+            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -1168,7 +1223,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

@@ -29,6 +29,8 @@ struct V2View {
   const int2* cta_cam;       // per CTA: [cam_lo, cam_hi) touched by its tiles
   const int2* cta_big;       // per CTA: [begin, end) into big_tiles: the >32-row points inside its row range
   const TileDesc* big_tiles; // one point each, 33..kTile rows
+  const uint32_t* tile_meta; // v4: [num tiles][kV4MetaWords] row words + own descriptor + descriptor of the tile that reuses the stage
+  int stage_x;               // v4: the CTA keeps x of its camera range in shared memory
   double* partials;          // [num_ctas][9 * max_cam_span]
   int num_ctas;
   int max_cam_span;
@@ -523,6 +525,155 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
     t_issue += v.warps;
   }
   schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x);
+  v2_epilogue(v, sy, cr, y);
+}
+
+// ------------------------------------------------------------------------------------------------
+// v4: every operand of a warp tile arrives through the warp's TMA ring -- the 2x9 F cells, the 2x3 E cells, the
+// (E'E+D^2)^-1 blocks of its points and a 160-byte descriptor block (row words, the tile's own extents and the extents
+// of the tile that will reuse the ring slot) -- and x of the CTA's camera range is staged once in shared memory, so the
+// main loop issues no global load at all (ncu on v3, profiles/r01_v3_schur_mul_l1723_ncu.txt: a third of all stall
+// samples were long-scoreboard waits on the row word -> x -> (E'E)^-1 dependency chain).  With 12 warps per SM the
+// register budget is 168, so the F cells are read from shared memory once and stay in registers.
+// ------------------------------------------------------------------------------------------------
+constexpr int kV4MaxThreads = 384;
+constexpr int kV4MetaWords = 40;
+constexpr int kV4StageBytes = 32 * 144 + 32 * 48 + 32 * 48 + kV4MetaWords * 4;  // F | E | P | descriptor block
+
+__host__ __device__ inline int v4_per_warp_bytes(int stages) { return stages * kV4StageBytes + 32 * kV2Scratch * 8 + ((8 * stages + 15) & ~15); }
+__host__ __device__ inline size_t v4_sx_bytes(int max_cam_span, int stage_x) { return stage_x ? v2_sy_stride(max_cam_span) * 8 : 0; }
+
+__device__ __forceinline__ void v4_issue(const V2View& v, const double* ete_inv, unsigned char* stage, uint64_t* bar, int tile,
+                                         int row_begin, int pt_begin, int row_count, int pt_count) {
+  mbar_arrive_expect_tx(bar, row_count * 192u + pt_count * 48u + kV4MetaWords * 4u);
+  bulk_g2s(stage, v.p.F() + 18 * static_cast<size_t>(row_begin), row_count * 144u, bar);
+  bulk_g2s(stage + 4608, v.p.E() + 6 * static_cast<size_t>(row_begin), row_count * 48u, bar);
+  bulk_g2s(stage + 6144, ete_inv + 6 * static_cast<size_t>(pt_begin), pt_count * 48u, bar);
+  bulk_g2s(stage + 7680, v.tile_meta + static_cast<size_t>(kV4MetaWords) * tile, kV4MetaWords * 4u, bar);
+}
+
+template <bool kStageX>
+__global__ void __launch_bounds__(kV4MaxThreads, 1)
+    schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
+                        const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* sy = reinterpret_cast<double*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = v.cta_part[blockIdx.x];
+  const int2 cr = v.cta_cam[blockIdx.x];
+  const int sy_stride = static_cast<int>(v2_sy_stride(v.max_cam_span));
+  const double* sx = sy + static_cast<size_t>(sy_stride) * v.replicas;
+  unsigned char* ring = smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas) + v4_sx_bytes(v.max_cam_span, kStageX ? 1 : 0);
+  unsigned char* wbase = ring + static_cast<size_t>(warp) * v.per_warp_bytes;
+  double* sW = reinterpret_cast<double*>(wbase + v.stages * kV4StageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 32 * kV2Scratch);
+  {
+    const int n = sy_stride * v.replicas;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = 0.0;
+    if (kStageX) {
+      double* sxw = sy + static_cast<size_t>(sy_stride) * v.replicas;
+      const double* xs = x + 9 * static_cast<size_t>(cr.x);
+      for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) sxw[i] = __ldg(xs + i);
+    }
+    if (lane == 0) {
+      for (int s = 0; s < v.stages; ++s) mbar_init(bars + s, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    if (lane == 0) {
+      int t = part.x + warp;
+      for (int s = 0; s < v.stages && t < part.y; ++s, t += v.warps) {
+        const WarpTile wt = v.wtiles[t];
+        v4_issue(v, ete_inv, wbase + s * kV4StageBytes, bars + s, t, wt.row_begin, wt.pt_begin, wt.row_count, wt.pt_count);
+      }
+    }
+  }
+  double* my_y = sy + (warp % v.replicas) * sy_stride;
+  const int reissue = v.warps * v.stages;
+  int it = 0;
+  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
+    const int s = it % v.stages;
+    const uint32_t parity = (it / v.stages) & 1;
+    unsigned char* stage = wbase + s * kV4StageBytes;
+    const double* sF = reinterpret_cast<const double*>(stage);
+    const double* sE = reinterpret_cast<const double*>(stage + 4608);
+    const double* sP = reinterpret_cast<const double*>(stage + 6144);
+    const uint32_t* sM = reinterpret_cast<const uint32_t*>(stage + 7680);
+    mbar_wait(bars + s, parity);
+    const uint4 own = *reinterpret_cast<const uint4*>(sM + 32);   // row_begin, pt_begin, rows | pts << 16, -
+    const uint4 nxt = *reinterpret_cast<const uint4*>(sM + 36);   // same for tile + warps * stages (rows == 0: none)
+    const int row_count = static_cast<int>(own.z & 0xffffu);
+    const bool active = lane < row_count;
+    const uint32_t meta = active ? sM[lane] : 0u;
+    const int cam = static_cast<int>(meta & 0x7fffffffu);
+    const Seg sg = v2_segment(active && (meta >> 31), row_count);
+    double f[18];
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      double xc[9];
+      if (kStageX) {
+        const double* xcp = sx + 9 * (cam - cr.x);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
+      } else {
+        const double* xcp = x + 9 * static_cast<size_t>(cam);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+      }
+      const double* fr = sF + lane * 18;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(fr + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+      e0 = lds2(sE + lane * 6);
+      e1 = lds2(sE + lane * 6 + 2);
+      e2 = lds2(sE + lane * 6 + 4);
+      double ta = 0.0, tb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t0 += f[2 * k] * xc[2 * k];
+        ta += f[2 * k + 1] * xc[2 * k + 1];
+        t1 += f[9 + 2 * k] * xc[2 * k];
+        tb += f[10 + 2 * k] * xc[2 * k + 1];
+      }
+      t0 += f[8] * xc[8];
+      t1 += f[17] * xc[8];
+      t0 += ta;
+      t1 += tb;
+      sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
+      sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
+      sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+    }
+    __syncwarp();
+    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      for (int j = sg.first; j < sg.end; ++j) {
+        u0 += sW[j * 3 + 0];
+        u1 += sW[j * 3 + 1];
+        u2 += sW[j * 3 + 2];
+      }
+      const double* pi = sP + 6 * sg.lpt;
+      const double2 pa = lds2(pi), pb = lds2(pi + 2), pc = lds2(pi + 4);
+      const double v0 = -(pa.x * u0 + pa.y * u1 + pb.x * u2);
+      const double v1 = -(pa.y * u0 + pb.y * u1 + pc.x * u2);
+      const double v2 = -(pb.x * u0 + pc.x * u1 + pc.y * u2);
+      t0 += e0.x * v0 + e0.y * v1 + e1.x * v2;
+      t1 += e1.y * v0 + e2.x * v1 + e2.y * v2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
+    }
+    __syncwarp();  // every lane is done with the ring slot and the scratch
+    if (lane == 0 && (nxt.z & 0xffffu) != 0u)
+      v4_issue(v, ete_inv, stage, bars + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
+               static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
+    cam_accumulate9(my_y, cam - cr.x, active, g);
+  }
+  schur_mul_big_points(v, ring, sy, cr, ete_inv, x);
   v2_epilogue(v, sy, cr, y);
 }
 
