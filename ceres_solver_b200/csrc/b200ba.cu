@@ -196,7 +196,7 @@ struct b200_handle {
   bool big_folded = false;   // S*x handles them inside schur_mul_v3_kernel (no extra launch)
   int2* d_cta_big = nullptr;
   uint32_t* d_tile_meta = nullptr;
-  bool mul_v4 = false;
+  bool mul_v4 = false, mul_v4_owned = false;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
@@ -456,7 +456,8 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
       }));
     OK(launch(h, K_SCHUR_MUL, [&] {
-      if (h->mul_v4) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true, true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      else if (h->mul_v4) schur_mul_v4_kernel<true, false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
     }));
@@ -578,7 +579,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v4) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true, true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        else if (h->mul_v4) schur_mul_v4_kernel<true, false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
@@ -1078,13 +1080,14 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       h->mul_smem = h->v2_smem;
     }
     // v4 (all operands through the TMA ring, x staged in shared memory): needs the narrow camera ranges of the
-    // direct-flush mode; 12 warps x 2 stages when they fit next to the private camera vector(s).
+    // direct-flush mode; up to 16 warps with a one-slot ring each, one private camera vector per warp when they fit.
     if (h->mul_v3 && h->v2.direct && getenv("B200_MUL_V3") == nullptr) {
       const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 2048;
       const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
       int w4 = kV4MaxThreads / 32;
       if (const char* e = getenv("B200_V4_WARPS")) w4 = std::max(4, std::min(w4, atoi(e)));
-      const int st4 = 2;
+      int st4 = 1;  // the slot is refilled as soon as its contents are in registers: one stage per warp, more warps
+      if (const char* e = getenv("B200_V4_STAGES")) st4 = std::max(1, std::min(3, atoi(e)));
       for (; w4 >= 8; --w4) {
         const long rem = total - static_cast<long>(w4) * v4_per_warp_bytes(st4) - sy1 /* staged x */;
         if (rem < sy1) continue;
@@ -1118,7 +1121,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->mul_smem = v2_sy_bytes(max_cam_span, rep4) + v4_sx_bytes(max_cam_span, 1) + static_cast<size_t>(w4) * h->v2_mul.per_warp_bytes;
         h->mul_v4 = true;
         h->big_folded = getenv("B200_DISABLE_BIG_FOLD") == nullptr;
-        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        h->mul_v4_owned = rep4 == w4;
+        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         break;
       }
     }
@@ -1171,7 +1176,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     fprintf(stderr,
             "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
             C, P, N, wtiles.size(), big_tiles.size(), max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
-            h->mul_v4 ? "v4" : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
+            h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
             h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());

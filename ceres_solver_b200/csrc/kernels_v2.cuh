@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
 // samples were long-scoreboard waits on the row word -> x -> (E'E)^-1 dependency chain).  With 12 warps per SM the
 // register budget is 168, so the F cells are read from shared memory once and stay in registers.
 // ------------------------------------------------------------------------------------------------
-constexpr int kV4MaxThreads = 384;
+constexpr int kV4MaxThreads = 512;
 constexpr int kV4MetaWords = 40;
 constexpr int kV4StageBytes = 32 * 144 + 32 * 48 + 32 * 48 + kV4MetaWords * 4;  // F | E | P | descriptor block
 
@@ -552,7 +552,37 @@ __device__ __forceinline__ void v4_issue(const V2View& v, const double* ete_inv,
   bulk_g2s(stage + 7680, v.tile_meta + static_cast<size_t>(kV4MetaWords) * tile, kV4MetaWords * 4u, bar);
 }
 
-template <bool kStageX>
+// Adds one 9-vector per row into replica `sy_rep` that only THIS warp touches: after the same warp-level
+// aggregation as cam_accumulate9 the group leaders hold distinct cameras, so plain read-modify-write is race-free
+// and the nine updates are independent (the shared-memory FP64 atomic is a CAS loop: nine dependent round trips).
+__device__ __forceinline__ void cam_accumulate9_owned(double* sy_rep, int cam_local, bool active, double (&g)[9]) {
+  const int lane = threadIdx.x & 31;
+  const int key = active ? cam_local : (0x40000000 | lane);
+  const unsigned m = __match_any_sync(0xffffffffu, key);
+  const unsigned above = (lane == 31) ? 0u : (m & (0xfffffffeu << lane));
+  int nxt = above ? (__ffs(above) - 1) : -1;
+  while (__any_sync(0xffffffffu, nxt >= 0)) {
+    const int src = nxt >= 0 ? nxt : lane;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const double v = __shfl_sync(0xffffffffu, g[k], src);
+      g[k] += (nxt >= 0) ? v : 0.0;
+    }
+    nxt = __shfl_sync(0xffffffffu, nxt, src);
+    nxt = (src == lane) ? -1 : nxt;
+  }
+  if (active && (m & ((1u << lane) - 1u)) == 0u) {
+    double* yc = sy_rep + 9 * cam_local;
+    double o[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = yc[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) yc[k] = o[k] + g[k];
+  }
+  __syncwarp();
+}
+
+template <bool kStageX, bool kOwned>
 __global__ void __launch_bounds__(kV4MaxThreads, 1)
     schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
                         const int* __restrict__ done_flag) {
@@ -569,27 +599,25 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
   double* sW = reinterpret_cast<double*>(wbase + v.stages * kV4StageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 32 * kV2Scratch);
   {
-    const int n = sy_stride * v.replicas;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = 0.0;
-    if (kStageX) {
-      double* sxw = sy + static_cast<size_t>(sy_stride) * v.replicas;
-      const double* xs = x + 9 * static_cast<size_t>(cr.x);
-      for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) sxw[i] = __ldg(xs + i);
-    }
     if (lane == 0) {
       for (int s = 0; s < v.stages; ++s) mbar_init(bars + s, 1);
       fence_mbar_init();
-    }
-    __syncthreads();
-    if (lane == 0) {
       int t = part.x + warp;
       for (int s = 0; s < v.stages && t < part.y; ++s, t += v.warps) {
         const WarpTile wt = v.wtiles[t];
         v4_issue(v, ete_inv, wbase + s * kV4StageBytes, bars + s, t, wt.row_begin, wt.pt_begin, wt.row_count, wt.pt_count);
       }
     }
+    const int n = sy_stride * v.replicas;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = 0.0;
+    if (kStageX) {
+      double* sxw = sy + static_cast<size_t>(sy_stride) * v.replicas;
+      const double* xs = x + 9 * static_cast<size_t>(cr.x);
+      for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) sxw[i] = __ldcg(xs + i);
+    }
+    __syncthreads();
   }
-  double* my_y = sy + (warp % v.replicas) * sy_stride;
+  double* my_y = sy + (kOwned ? warp : warp % v.replicas) * sy_stride;
   const int reissue = v.warps * v.stages;
   int it = 0;
   for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
@@ -601,6 +629,8 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     const double* sP = reinterpret_cast<const double*>(stage + 6144);
     const uint32_t* sM = reinterpret_cast<const uint32_t*>(stage + 7680);
     mbar_wait(bars + s, parity);
+    // ---- everything the tile needs from its ring slot goes to registers first, so that the slot can be refilled
+    //      while the arithmetic runs (the ring needs a single stage per warp: more resident warps instead)
     const uint4 own = *reinterpret_cast<const uint4*>(sM + 32);   // row_begin, pt_begin, rows | pts << 16, -
     const uint4 nxt = *reinterpret_cast<const uint4*>(sM + 36);   // same for tile + warps * stages (rows == 0: none)
     const int row_count = static_cast<int>(own.z & 0xffffu);
@@ -609,19 +639,8 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     const int cam = static_cast<int>(meta & 0x7fffffffu);
     const Seg sg = v2_segment(active && (meta >> 31), row_count);
     double f[18];
-    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
-    double t0 = 0.0, t1 = 0.0;
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0, pa = e0, pb = e0, pc = e0;
     if (active) {
-      double xc[9];
-      if (kStageX) {
-        const double* xcp = sx + 9 * (cam - cr.x);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
-      } else {
-        const double* xcp = x + 9 * static_cast<size_t>(cam);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
-      }
       const double* fr = sF + lane * 18;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
@@ -632,6 +651,27 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
       e0 = lds2(sE + lane * 6);
       e1 = lds2(sE + lane * 6 + 2);
       e2 = lds2(sE + lane * 6 + 4);
+      const double* pi = sP + 6 * sg.lpt;
+      pa = lds2(pi);
+      pb = lds2(pi + 2);
+      pc = lds2(pi + 4);
+    }
+    __syncwarp();  // every lane is done with the ring slot (and with the previous tile's scratch)
+    if (lane == 0 && (nxt.z & 0xffffu) != 0u)
+      v4_issue(v, ete_inv, stage, bars + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
+               static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      double xc[9];
+      if (kStageX) {
+        const double* xcp = sx + 9 * (cam - cr.x);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
+      } else {
+        const double* xcp = x + 9 * static_cast<size_t>(cam);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) xc[k] = __ldcg(xcp + k);
+      }
       double ta = 0.0, tb = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -657,8 +697,6 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
         u1 += sW[j * 3 + 1];
         u2 += sW[j * 3 + 2];
       }
-      const double* pi = sP + 6 * sg.lpt;
-      const double2 pa = lds2(pi), pb = lds2(pi + 2), pc = lds2(pi + 4);
       const double v0 = -(pa.x * u0 + pa.y * u1 + pb.x * u2);
       const double v1 = -(pa.y * u0 + pb.y * u1 + pc.x * u2);
       const double v2 = -(pb.x * u0 + pc.x * u1 + pc.y * u2);
@@ -667,11 +705,8 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
 #pragma unroll
       for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
     }
-    __syncwarp();  // every lane is done with the ring slot and the scratch
-    if (lane == 0 && (nxt.z & 0xffffu) != 0u)
-      v4_issue(v, ete_inv, stage, bars + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
-               static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
-    cam_accumulate9(my_y, cam - cr.x, active, g);
+    if (kOwned) cam_accumulate9_owned(my_y, cam - cr.x, active, g);
+    else cam_accumulate9(my_y, cam - cr.x, active, g);
   }
   schur_mul_big_points(v, ring, sy, cr, ete_inv, x);
   v2_epilogue(v, sy, cr, y);
