@@ -31,6 +31,7 @@
 #include "kernels_v2b.cuh"
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
+#include "pcg_kernel.cuh"
 
 using namespace b200;
 
@@ -77,6 +78,7 @@ enum KernelId {
   K_BACKSUB,
   K_MODEL_COST,
   K_CG_VEC,
+  K_PCG,
   K_LM_VEC,
   K_MISC,
   K_COUNT
@@ -84,7 +86,7 @@ enum KernelId {
 const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squared_column_norm", "scale_columns",
                                      "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
                                      "schur_multiply", "schur_multiply_big_points", "camera_reduce", "schur_diag_blocks", "invert_9x9", "back_substitute",
-                                     "model_cost", "cg_vector", "lm_vector", "misc"};
+                                     "model_cost", "cg_vector", "pcg_persistent", "lm_vector", "misc"};
 
 #ifdef B200_WITH_NCCL
 // NCCL is bound lazily with dlopen/dlsym, and only when world_size > 1: the library then shares whatever
@@ -197,6 +199,10 @@ struct b200_handle {
   int2* d_cta_big = nullptr;
   uint32_t* d_tile_meta = nullptr;
   bool mul_v4 = false, mul_v4_owned = false;
+  bool pcg_ok = false;       // the whole PCG runs as one persistent cooperative kernel (pcg_kernel.cuh)
+  int pcg_cams_per_cta = 0;
+  double *d_qa = nullptr, *d_qb = nullptr, *d_pcg_red = nullptr;
+  unsigned* d_pcg_barrier = nullptr;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
@@ -456,8 +462,8 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
       }));
     OK(launch(h, K_SCHUR_MUL, [&] {
-      if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true, true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
-      else if (h->mul_v4) schur_mul_v4_kernel<true, false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
     }));
@@ -552,6 +558,18 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   va.p = h->d_p;
   va.red = h->d_red;
   va.st = h->d_cg;
+  auto finish = [&]() -> int {
+    summary->num_iterations = h->h_cg->iteration;
+    summary->termination_type = h->h_cg->termination;
+    summary->residual_norm = h->h_cg->norm_r;
+    if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR) {
+      OK(launch(h, K_BACKSUB, [&] {
+        backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, d_b, h->d_sol, d_x);
+      }));
+      CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    return B200_OK;
+  };
   // In direct-flush mode the vector kernel pre-seeds the next product's output (D_f^2 p, rank 0 only) and the product
   // kernels RED straight into it: one product launch + one vector launch per iteration.
   const bool seeded = h->v2_ok && h->v2.direct;
@@ -579,8 +597,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true, true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
-        else if (h->mul_v4) schur_mul_v4_kernel<true, false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
@@ -596,11 +614,65 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
   };
+  if (h->pcg_ok && !h->profiling) {
+    // single persistent kernel: product, vector updates and termination tests of every iteration (pcg_kernel.cuh)
+    PcgArgs pa{};
+    pa.v = h->v2_mul;
+    pa.ete_inv = h->d_ete_inv;
+    pa.prm = prm;
+    pa.prm.max_iterations = std::max(o->max_num_iterations, 1);
+    pa.C = h->C;
+    pa.cams_per_cta = h->pcg_cams_per_cta;
+    pa.reset_period = o->residual_reset_period > 0 ? o->residual_reset_period : 0;
+    pa.precond = precond;
+    pa.Df = Df;
+    pa.minv = h->d_minv;
+    pa.rhs = h->d_rhs;
+    pa.x = h->d_sol;
+    pa.r = h->d_r;
+    pa.z = h->d_z;
+    pa.p = h->d_p;
+    pa.qa = h->d_qa;
+    pa.qb = h->d_qb;
+    pa.tmp = h->d_tmp;
+    pa.red = h->d_pcg_red;
+    pa.st = h->d_cg;
+    pa.barrier = h->d_pcg_barrier;
+    const char* trace_path = getenv("B200_PCG_TRACE");
+    const int trace_iters = 64;
+    unsigned long long* d_trace = nullptr;
+    if (trace_path != nullptr) {
+      OK(dev_alloc(&d_trace, static_cast<size_t>(h->v2.num_ctas) * trace_iters * 8));
+      CU(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * h->v2.num_ctas * trace_iters * 8, h->stream));
+      pa.trace = d_trace;
+      pa.trace_iters = trace_iters;
+    }
+    CU(cudaMemsetAsync(h->d_pcg_barrier, 0, 4 * sizeof(unsigned), h->stream));
+    void* args[] = {&pa};
+    OK(launch(h, K_PCG, [&] {
+      if (h->mul_v4_owned)
+        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pcg_kernel<true>), dim3(h->v2.num_ctas), dim3(32 * h->v2_mul.warps), args, h->mul_smem, h->stream);
+      else
+        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pcg_kernel<false>), dim3(h->v2.num_ctas), dim3(32 * h->v2_mul.warps), args, h->mul_smem, h->stream);
+    }));
+    CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (d_trace != nullptr) {  // debugging aid: phase time stamps of the first iterations, one file per solve (overwritten)
+      std::vector<unsigned long long> tr(static_cast<size_t>(h->v2.num_ctas) * trace_iters * 8);
+      CU(cudaMemcpy(tr.data(), d_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(trace_path, "wb")) {
+        fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f);
+        fclose(f);
+      }
+      cudaFree(d_trace);
+    }
+    return finish();
+  }
   OK(vec(CG_BEGIN, h->d_z, h->d_z));
   const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
   // Termination is decided on the device; the host only polls the state every few iterations
   // (kernels become no-ops once done is set), so there is no per-iteration synchronisation.
-  int check_every = 2;
+  int check_every = h->profiling ? 1 : 2;  // (profiling: no launches after termination, they would skew the means)
   bool done = false;
   int it = 0;
   const int max_it = std::max(o->max_num_iterations, 1);
@@ -620,18 +692,9 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     done = h->h_cg->done != 0 || it >= max_it;
-    check_every = std::min(check_every * 2, 8);
+    if (!h->profiling) check_every = std::min(check_every * 2, 8);
   }
-  summary->num_iterations = h->h_cg->iteration;
-  summary->termination_type = h->h_cg->termination;
-  summary->residual_norm = h->h_cg->norm_r;
-  if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR) {
-    OK(launch(h, K_BACKSUB, [&] {
-      backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, d_b, h->d_sol, d_x);
-    }));
-    CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
-  }
-  return B200_OK;
+  return finish();
 }
 
 int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks = false) {
@@ -844,19 +907,43 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2), cta_big(num_ctas_v2, make_int2(0, 0));
   int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1, mul_warps = 0, mul_stages = 0, mul_replicas = 1;
   if (v2_possible && !wtiles.empty()) {
-    // Static partition by row position: CTA b owns the warp tiles (and the >32-row points) that start inside
-    // rows [N*b/n, N*(b+1)/n), so that neighbouring CTAs stream neighbouring HBM ranges and the big points add
-    // to the balance of the CTA that takes them.
+    // Static partition by position in the row order, balanced by cost: a warp tile costs about the same whatever its
+    // fill (the kernels are bound by warp-instruction issue / LSU work, not by bytes), and a >32-row point, which the
+    // whole CTA processes serially, costs as much as ~20 tiles (in-kernel time stamps, profiles/r01_pcg_persistent_trace_l1723.txt).
+    // CTA b owns the items whose cumulative cost starts in [total * b / n, total * (b + 1) / n): neighbouring CTAs stream
+    // neighbouring HBM ranges and touch neighbouring cameras.
     const int T = static_cast<int>(wtiles.size());
-    auto owner = [&](int row) { return static_cast<int>(static_cast<long>(row) * num_ctas_v2 / std::max(N, 1)); };
     {
-      int t = 0, g = 0;
-      for (int b = 0; b < num_ctas_v2; ++b) {
-        const int t0 = t, g0 = g;
-        while (t < T && owner(wtiles[t].row_begin) <= b) ++t;
-        while (g < static_cast<int>(big_tiles.size()) && owner(big_tiles[g].obs_begin) <= b) ++g;
-        cta_part[b] = make_int2(t0, t);
-        cta_big[b] = make_int2(g0, g);
+      double big_cost = 22.0;
+      if (const char* e = getenv("B200_BIG_COST")) big_cost = std::max(0.0, atof(e));
+      const double total_cost = T + big_cost * big_tiles.size();
+      int t = 0, g = 0, b = 0;
+      double cum = 0.0;
+      std::vector<int> t_end(num_ctas_v2, 0), g_end(num_ctas_v2, 0);
+      const int G = static_cast<int>(big_tiles.size());
+      while (t < T || g < G) {
+        const bool take_big = g < G && (t >= T || big_tiles[g].obs_begin < wtiles[t].row_begin);
+        const int owner = std::min(num_ctas_v2 - 1, static_cast<int>(cum * num_ctas_v2 / std::max(total_cost, 1.0)));
+        while (b < owner) {
+          t_end[b] = t;
+          g_end[b] = g;
+          ++b;
+        }
+        if (take_big) {
+          ++g;
+          cum += big_cost;
+        } else {
+          ++t;
+          cum += 1.0;
+        }
+      }
+      for (; b < num_ctas_v2; ++b) {
+        t_end[b] = T;
+        g_end[b] = G;
+      }
+      for (int k = 0; k < num_ctas_v2; ++k) {
+        cta_part[k] = make_int2(k == 0 ? 0 : t_end[k - 1], t_end[k]);
+        cta_big[k] = make_int2(k == 0 ? 0 : g_end[k - 1], g_end[k]);
       }
     }
     for (int b = 0; b < num_ctas_v2; ++b) {
@@ -1122,8 +1209,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->mul_v4 = true;
         h->big_folded = getenv("B200_DISABLE_BIG_FOLD") == nullptr;
         h->mul_v4_owned = rep4 == w4;
-        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_mul_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         break;
       }
     }
@@ -1131,6 +1220,25 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     h->v2_ok = true;
+    // Opt-in experiment (B200_PCG_PERSISTENT=1): the whole PCG as one persistent kernel.  Measured SLOWER than one
+    // product launch + one vector launch per iteration (59 vs 43 us per iteration on Ladybug-1723: software grid
+    // barriers and the serial vector phases on 148 fat CTAs cost more than two kernel boundaries; see
+    // profiles/r01_pcg_persistent_trace_l1723.txt), so the multi-kernel PCG stays the default.
+    if (h->mul_v4 && h->world == 1 && h->big_folded && getenv("B200_PCG_PERSISTENT") != nullptr) {
+      const int cpc = (C + num_ctas_v2 - 1) / num_ctas_v2;
+      int per_sm = 0;
+      if (h->mul_v4_owned) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<true>, 32 * h->v2_mul.warps, h->mul_smem));
+      else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, 32 * h->v2_mul.warps, h->mul_smem));
+      if (9 * cpc <= 32 * h->v2_mul.warps && per_sm >= 1 && prop.cooperativeLaunch) {
+        OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
+        OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
+        OK(dev_alloc(&h->d_pcg_red, static_cast<size_t>(num_ctas_v2) * 8));
+        OK(dev_alloc(&h->d_pcg_barrier, 4));
+        CU(cudaMemsetAsync(h->d_pcg_red, 0, sizeof(double) * num_ctas_v2 * 8, h->stream));
+        h->pcg_cams_per_cta = cpc;
+        h->pcg_ok = true;
+      }
+    }
     if (h->v2.direct && getenv("B200_DISABLE_V2B") == nullptr) {
       const size_t lim = prop.sharedMemPerBlockOptin - 2048;
       // Each kernel gets as many replicas of its private accumulators as fit next to its per-warp buffers
@@ -1174,10 +1282,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
 
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
-            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d\n",
             C, P, N, wtiles.size(), big_tiles.size(), max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
             h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
-            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0);
+            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->pcg_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -1228,7 +1336,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

@@ -314,39 +314,51 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
 // warp tiles (the warps' TMA rings are idle by then and provide the staging memory), one point at a time:
 // u = sum_rows E'(F x) through a CTA reduction, then the same update as the warp path, accumulated into the
 // CTA-private camera vector.  Every thread of the CTA must call this (it contains CTA barriers).
-__device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned char* ring, double* sy_rep0, int2 cr,
-                                                     const double* __restrict__ ete_inv, const double* __restrict__ x) {
+// x of camera `cam` is read at xbase + 9 * (cam - cam0): the global vector (cam0 = 0) or the CTA's staged range.
+// Staging layout: rows are staged in chunks of `chunk_rows`; chunk k lives at base + k * chunk_stride as
+// [chunk_rows x 18 F][chunk_rows x 6 E].  sU: 16 doubles of scratch, bar: an INITIALISED mbarrier whose current phase
+// parity is *parity_io (updated on return; only thread 0's copy matters to the caller).
+struct BigStage {
+  unsigned char* base;
+  int chunk_rows;
+  int chunk_stride;
+  double* sU;
+  uint64_t* bar;
+};
+
+__device__ __forceinline__ void schur_mul_big_points_impl(const V2View& v, const BigStage& st, uint32_t& parity, double* sy_rep0,
+                                                          int2 cr, const double* __restrict__ ete_inv, const double* xbase,
+                                                          int cam0) {
   const int2 br = v.cta_big[blockIdx.x];
-  if (br.y <= br.x) return;  // uniform per CTA
-  double* sF = reinterpret_cast<double*>(ring);
-  double* sE = sF + kTile * 18;
-  double* sU = sE + kTile * 6;                 // [4 warps][3] partial sums + [3] result
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sU + 16);
   const int tid = threadIdx.x;
-  __syncthreads();
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  uint32_t parity = 0;
+  double* sU = st.sU;
   for (int b = br.x; b < br.y; ++b) {
     const TileDesc d = v.big_tiles[b];
     if (tid == 0) {
-      mbar_arrive_expect_tx(bar, d.obs_count * 192u);
-      bulk_g2s(sE, v.p.E() + 6 * static_cast<size_t>(d.obs_begin), d.obs_count * 48u, bar);
-      bulk_g2s(sF, v.p.F() + 18 * static_cast<size_t>(d.obs_begin), d.obs_count * 144u, bar);
+      mbar_arrive_expect_tx(st.bar, d.obs_count * 192u);
+      for (int r0 = 0, k = 0; r0 < d.obs_count; r0 += st.chunk_rows, ++k) {
+        const int rows = min(st.chunk_rows, d.obs_count - r0);
+        unsigned char* dst = st.base + static_cast<size_t>(k) * st.chunk_stride;
+        bulk_g2s(dst, v.p.F() + 18 * static_cast<size_t>(d.obs_begin + r0), rows * 144u, st.bar);
+        bulk_g2s(dst + st.chunk_rows * 144, v.p.E() + 6 * static_cast<size_t>(d.obs_begin + r0), rows * 48u, st.bar);
+      }
     }
     const bool active = tid < d.obs_count;
+    const int chunk = tid / st.chunk_rows, rr = tid - chunk * st.chunk_rows;
+    const double* sF = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride) + rr * 18;
+    const double* sE = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride + st.chunk_rows * 144) + rr * 6;
     int cam = 0;
     double xc[9];
-    if (active) {
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0;
+    if (active) {  // everything that does not come through the bulk copy is requested while it is in flight
       cam = static_cast<int>(__ldg(v.row_meta + d.obs_begin + tid) & 0x7fffffffu);
-      const double* xcp = x + 9 * static_cast<size_t>(cam);
+      const double* pi = ete_inv + 6 * static_cast<size_t>(d.pt_begin);
+      p0 = __ldg(pi), p1 = __ldg(pi + 1), p2 = __ldg(pi + 2), p3 = __ldg(pi + 3), p4 = __ldg(pi + 4), p5 = __ldg(pi + 5);
+      const double* xcp = xbase + 9 * static_cast<size_t>(cam - cam0);
 #pragma unroll
-      for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
+      for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
     }
-    mbar_wait(bar, parity);
+    mbar_wait(st.bar, parity);
     parity ^= 1;
     double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
     double f[18];
@@ -354,7 +366,7 @@ __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned c
     if (active) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        const double2 a = lds2(sF + tid * 18 + 2 * k);
+        const double2 a = lds2(sF + 2 * k);
         f[2 * k] = a.x;
         f[2 * k + 1] = a.y;
       }
@@ -363,9 +375,9 @@ __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned c
         t0 += f[k] * xc[k];
         t1 += f[9 + k] * xc[k];
       }
-      e0 = lds2(sE + tid * 6);
-      e1 = lds2(sE + tid * 6 + 2);
-      e2 = lds2(sE + tid * 6 + 4);
+      e0 = lds2(sE);
+      e1 = lds2(sE + 2);
+      e2 = lds2(sE + 4);
       w0 = e0.x * t0 + e1.y * t1;
       w1 = e0.y * t0 + e2.x * t1;
       w2 = e1.x * t0 + e2.y * t1;
@@ -386,8 +398,6 @@ __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned c
     __syncthreads();
     if (active) {
       const double u0 = sU[0] + sU[3] + sU[6] + sU[9], u1 = sU[1] + sU[4] + sU[7] + sU[10], u2 = sU[2] + sU[5] + sU[8] + sU[11];
-      const double* pi = ete_inv + 6 * static_cast<size_t>(d.pt_begin);
-      const double p0 = __ldg(pi), p1 = __ldg(pi + 1), p2 = __ldg(pi + 2), p3 = __ldg(pi + 3), p4 = __ldg(pi + 4), p5 = __ldg(pi + 5);
       const double v0 = -(p0 * u0 + p1 * u1 + p2 * u2);
       const double v1 = -(p1 * u0 + p3 * u1 + p4 * u2);
       const double v2 = -(p2 * u0 + p4 * u1 + p5 * u2);
@@ -399,6 +409,28 @@ __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned c
     }
     __syncthreads();  // staging and sU are reused by the next point
   }
+}
+
+// v2/v3 layout: the (idle) ring is used as one contiguous staging area; the kernel ends afterwards, so overwriting the
+// warps' barriers is harmless.
+__device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned char* ring, double* sy_rep0, int2 cr,
+                                                     const double* __restrict__ ete_inv, const double* xbase, int cam0) {
+  const int2 br = v.cta_big[blockIdx.x];
+  if (br.y <= br.x) return;  // uniform per CTA
+  BigStage st;
+  st.base = ring;
+  st.chunk_rows = kTile;
+  st.chunk_stride = kTile * 192;
+  st.sU = reinterpret_cast<double*>(ring + kTile * 192);
+  st.bar = reinterpret_cast<uint64_t*>(st.sU + 16);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_init(st.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  schur_mul_big_points_impl(v, st, parity, sy_rep0, cr, ete_inv, xbase, cam0);
 }
 
 constexpr int kV3MaxThreads = 512;
@@ -524,7 +556,7 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
   }
-  schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x);
+  schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x, 0);
   v2_epilogue(v, sy, cr, y);
 }
 
@@ -540,7 +572,10 @@ constexpr int kV4MaxThreads = 512;
 constexpr int kV4MetaWords = 40;
 constexpr int kV4StageBytes = 32 * 144 + 32 * 48 + 32 * 48 + kV4MetaWords * 4;  // F | E | P | descriptor block
 
-__host__ __device__ inline int v4_per_warp_bytes(int stages) { return stages * kV4StageBytes + 32 * kV2Scratch * 8 + ((8 * stages + 15) & ~15); }
+// [stages x slot][scratch 96 doubles][slot barriers][16 B: warp 0 keeps the barrier + parity word of the >32-row points]
+__host__ __device__ inline int v4_bars_offset(int stages) { return stages * kV4StageBytes + 32 * kV2Scratch * 8; }
+__host__ __device__ inline int v4_extra_offset(int stages) { return v4_bars_offset(stages) + ((8 * stages + 15) & ~15); }
+__host__ __device__ inline int v4_per_warp_bytes(int stages) { return v4_extra_offset(stages) + 16; }
 __host__ __device__ inline size_t v4_sx_bytes(int max_cam_span, int stage_x) { return stage_x ? v2_sy_stride(max_cam_span) * 8 : 0; }
 
 __device__ __forceinline__ void v4_issue(const V2View& v, const double* ete_inv, unsigned char* stage, uint64_t* bar, int tile,
@@ -582,53 +617,115 @@ __device__ __forceinline__ void cam_accumulate9_owned(double* sy_rep, int cam_lo
   __syncwarp();
 }
 
-template <bool kStageX, bool kOwned>
-__global__ void __launch_bounds__(kV4MaxThreads, 1)
-    schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
-                        const int* __restrict__ done_flag) {
-  if (done_flag != nullptr && *done_flag != 0) return;
+// Shared-memory map of a v4 CTA: [replicas of the private camera vector][x of the camera range][per-warp areas],
+// per-warp area = [stages x {F | E | P | descriptor block}][exchange scratch 96 doubles][mbarriers].
+// The context holds OFFSETS into the dynamic shared memory, not pointers: a pointer that crosses a (non-inlined)
+// function boundary loses its address space and every access through it becomes a generic LD/ST instead of LDS/STS.
+__device__ __forceinline__ unsigned char* v4_smem() {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sy = reinterpret_cast<double*>(smem_raw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int2 part = v.cta_part[blockIdx.x];
-  const int2 cr = v.cta_cam[blockIdx.x];
-  const int sy_stride = static_cast<int>(v2_sy_stride(v.max_cam_span));
-  const double* sx = sy + static_cast<size_t>(sy_stride) * v.replicas;
-  unsigned char* ring = smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas) + v4_sx_bytes(v.max_cam_span, kStageX ? 1 : 0);
-  unsigned char* wbase = ring + static_cast<size_t>(warp) * v.per_warp_bytes;
-  double* sW = reinterpret_cast<double*>(wbase + v.stages * kV4StageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + 32 * kV2Scratch);
-  {
-    if (lane == 0) {
-      for (int s = 0; s < v.stages; ++s) mbar_init(bars + s, 1);
-      fence_mbar_init();
-      int t = part.x + warp;
-      for (int s = 0; s < v.stages && t < part.y; ++s, t += v.warps) {
-        const WarpTile wt = v.wtiles[t];
-        v4_issue(v, ete_inv, wbase + s * kV4StageBytes, bars + s, t, wt.row_begin, wt.pt_begin, wt.row_count, wt.pt_count);
-      }
+  return smem_raw;
+}
+struct V4Ctx {
+  int sy_stride;
+  int sx_off, ring_off, wbase_off, sW_off, bars_off;
+  int2 part, cr;
+  __device__ __forceinline__ double* sy() const { return reinterpret_cast<double*>(v4_smem()); }
+  __device__ __forceinline__ double* sx() const { return reinterpret_cast<double*>(v4_smem() + sx_off); }
+  __device__ __forceinline__ unsigned char* ring() const { return v4_smem() + ring_off; }
+  __device__ __forceinline__ unsigned char* wbase() const { return v4_smem() + wbase_off; }
+  __device__ __forceinline__ double* sW() const { return reinterpret_cast<double*>(v4_smem() + sW_off); }
+  __device__ __forceinline__ uint64_t* bars() const { return reinterpret_cast<uint64_t*>(v4_smem() + bars_off); }
+};
+
+__device__ __forceinline__ V4Ctx v4_ctx(const V2View& v) {
+  V4Ctx c;
+  const int warp = threadIdx.x >> 5;
+  c.sy_stride = static_cast<int>(v2_sy_stride(v.max_cam_span));
+  c.sx_off = static_cast<int>(v2_sy_bytes(v.max_cam_span, v.replicas));
+  c.ring_off = c.sx_off + static_cast<int>(v4_sx_bytes(v.max_cam_span, 1));
+  c.wbase_off = c.ring_off + warp * v.per_warp_bytes;
+  c.sW_off = c.wbase_off + v.stages * kV4StageBytes;
+  c.bars_off = c.sW_off + 32 * kV2Scratch * 8;
+  c.part = v.cta_part[blockIdx.x];
+  c.cr = v.cta_cam[blockIdx.x];
+  return c;
+}
+
+// Barriers are initialised ONCE per kernel (re-initialising a live mbarrier is undefined); a kernel that runs several
+// products keeps them and tracks the phase parity of every ring slot in `flip` (bit s = parity of the next phase of
+// slot s).  The >32-row points use one more barrier and a parity word in warp 0's scratch.
+constexpr int kV4BigChunkRows = 40;  // 40 rows x 192 B = 7680 B: one chunk per warp slot
+__device__ __forceinline__ void v4_init(const V2View& v, const V4Ctx& c) {
+  if ((threadIdx.x & 31) == 0) {
+    for (int s = 0; s < v.stages; ++s) mbar_init(c.bars() + s, 1);
+    if (threadIdx.x == 0) {
+      unsigned char* extra = c.ring() + v4_extra_offset(v.stages);  // warp 0's spare words
+      mbar_init(reinterpret_cast<uint64_t*>(extra), 1);
+      *reinterpret_cast<uint32_t*>(extra + 8) = 0u;
     }
-    const int n = sy_stride * v.replicas;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) sy[i] = 0.0;
-    if (kStageX) {
-      double* sxw = sy + static_cast<size_t>(sy_stride) * v.replicas;
-      const double* xs = x + 9 * static_cast<size_t>(cr.x);
-      for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) sxw[i] = __ldcg(xs + i);
-    }
-    __syncthreads();
+    fence_mbar_init();
   }
-  double* my_y = sy + (kOwned ? warp : warp % v.replicas) * sy_stride;
+}
+
+// Requests the warp's first tiles.  Its ring slots must be idle.
+__device__ __forceinline__ void v4_prime(const V2View& v, const double* ete_inv, const V4Ctx& c) {
+  if ((threadIdx.x & 31) == 0) {
+    int t = c.part.x + (threadIdx.x >> 5);
+    for (int s = 0; s < v.stages && t < c.part.y; ++s, t += v.warps) {
+      const WarpTile wt = v.wtiles[t];
+      v4_issue(v, ete_inv, c.wbase() + s * kV4StageBytes, c.bars() + s, t, wt.row_begin, wt.pt_begin, wt.row_count, wt.pt_count);
+    }
+  }
+}
+
+// Waits for the tiles requested by v4_prime without consuming them (before the CTA exits).
+__device__ __forceinline__ void v4_drain(const V2View& v, const V4Ctx& c, uint32_t flip) {
+  int t = c.part.x + (threadIdx.x >> 5);
+  for (int s = 0; s < v.stages && t < c.part.y; ++s, t += v.warps) mbar_wait(c.bars() + s, (flip >> s) & 1u);
+}
+
+// The >32-row points of the CTA on the v4 layout: staged in 40-row chunks, one per warp slot (slots 0..3), scratch
+// in warp 0's scratch words [64, 80), barrier + parity in its spare words -- nothing a later product needs is
+// overwritten.
+__device__ __forceinline__ void v4_big_points(const V2View& v, const V4Ctx& c, const double* __restrict__ ete_inv) {
+  const int2 br = v.cta_big[blockIdx.x];
+  if (br.y <= br.x) return;  // uniform per CTA
+  double* sw0 = reinterpret_cast<double*>(c.ring() + v.stages * kV4StageBytes);
+  BigStage st;
+  st.base = c.ring();
+  st.chunk_rows = kV4BigChunkRows;
+  st.chunk_stride = v.per_warp_bytes;
+  st.sU = sw0 + 64;
+  unsigned char* extra = c.ring() + v4_extra_offset(v.stages);
+  st.bar = reinterpret_cast<uint64_t*>(extra);
+  uint32_t* pword = reinterpret_cast<uint32_t*>(extra + 8);
+  __syncthreads();  // every warp is done with its ring slot and scratch
+  uint32_t parity = *pword;
+  schur_mul_big_points_impl(v, st, parity, c.sy(), c.cr, ete_inv, c.sx(), c.cr.x);
+  if (threadIdx.x == 0) *pword = parity;
+}
+
+// The warp-tile loop: accumulates F'(F x - E P E'F x) of the CTA's tiles into the private camera vector(s).
+// Expects primed barriers, zeroed c.sy(), x of the camera range in c.sx(), and a CTA barrier after those.
+// `flip` carries the slots' phase parities from one product to the next (0 for a kernel that runs a single product).
+template <bool kOwned>
+__device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv, const V4Ctx& c, uint32_t& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = c.part, cr = c.cr;
+  const double* sx = c.sx();
+  double* sW = c.sW();
+  double* my_y = c.sy() + (kOwned ? warp : warp % v.replicas) * c.sy_stride;
   const int reissue = v.warps * v.stages;
   int it = 0;
   for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
     const int s = it % v.stages;
-    const uint32_t parity = (it / v.stages) & 1;
-    unsigned char* stage = wbase + s * kV4StageBytes;
+    const uint32_t parity = ((it / v.stages) ^ (flip >> s)) & 1u;
+    unsigned char* stage = c.wbase() + s * kV4StageBytes;
     const double* sF = reinterpret_cast<const double*>(stage);
     const double* sE = reinterpret_cast<const double*>(stage + 4608);
     const double* sP = reinterpret_cast<const double*>(stage + 6144);
     const uint32_t* sM = reinterpret_cast<const uint32_t*>(stage + 7680);
-    mbar_wait(bars + s, parity);
+    mbar_wait(c.bars() + s, parity);
     // ---- everything the tile needs from its ring slot goes to registers first, so that the slot can be refilled
     //      while the arithmetic runs (the ring needs a single stage per warp: more resident warps instead)
     const uint4 own = *reinterpret_cast<const uint4*>(sM + 32);   // row_begin, pt_begin, rows | pts << 16, -
@@ -658,20 +755,14 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     }
     __syncwarp();  // every lane is done with the ring slot (and with the previous tile's scratch)
     if (lane == 0 && (nxt.z & 0xffffu) != 0u)
-      v4_issue(v, ete_inv, stage, bars + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
+      v4_issue(v, ete_inv, stage, c.bars() + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
                static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
     double t0 = 0.0, t1 = 0.0;
     if (active) {
       double xc[9];
-      if (kStageX) {
-        const double* xcp = sx + 9 * (cam - cr.x);
+      const double* xcp = sx + 9 * (cam - cr.x);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
-      } else {
-        const double* xcp = x + 9 * static_cast<size_t>(cam);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) xc[k] = __ldcg(xcp + k);
-      }
+      for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
       double ta = 0.0, tb = 0.0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -708,8 +799,29 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     if (kOwned) cam_accumulate9_owned(my_y, cam - cr.x, active, g);
     else cam_accumulate9(my_y, cam - cr.x, active, g);
   }
-  schur_mul_big_points(v, ring, sy, cr, ete_inv, x);
-  v2_epilogue(v, sy, cr, y);
+  // phases consumed on slot s: tiles it = s, s + stages, ... < `it`
+  for (int s = 0; s < v.stages; ++s) flip ^= (((it - s + v.stages - 1) / v.stages) & 1u) << s;
+}
+
+template <bool kOwned>
+__global__ void __launch_bounds__(kV4MaxThreads, 1)
+    schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
+                        const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && *done_flag != 0) return;
+  const V4Ctx c = v4_ctx(v);
+  v4_init(v, c);
+  v4_prime(v, ete_inv, c);
+  {
+    const int n = c.sy_stride * v.replicas;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c.sy()[i] = 0.0;
+    const double* xs = x + 9 * static_cast<size_t>(c.cr.x);
+    for (int i = threadIdx.x; i < 9 * (c.cr.y - c.cr.x); i += blockDim.x) c.sx()[i] = __ldcg(xs + i);
+  }
+  __syncthreads();
+  uint32_t flip = 0;
+  v4_tiles<kOwned>(v, ete_inv, c, flip);
+  v4_big_points(v, c, ete_inv);
+  v2_epilogue(v, c.sy(), c.cr, y);
 }
 
 // ------------------------------------------------------------------------------------------------
