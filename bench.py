@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_TRAFFIC = {("ladybug-1723", "schur_multiply"): 141.14e6 + 3.62e6, ("venice-1778", "schur_multiply"): 1030.5e6 + 3.9e6}
+NCU_TRAFFIC = {("ladybug-1723", "schur_multiply"): 141.92e6 + 4.14e6, ("venice-1778", "schur_multiply"): 1036.3e6 + 4.2e6}
 
 METRIC = "lm_iterations_per_sec"
 UNIT = "LM iterations/s"
