@@ -111,6 +111,7 @@ bool B200Evaluator::Evaluate(const Evaluator::EvaluateOptions&, const double* st
   ScopedExecutionTimer kind(gradient == nullptr && jacobian == nullptr ? "Evaluator::Residual" : "Evaluator::Jacobian",
                             &execution_summary_);  // the keys Solver::Summary reads (solver.cc:615-628)
   const int rc = b200_evaluate(ctx_->handle, state, cost, residuals, gradient, jacobian != nullptr);
+  if (residuals != nullptr) ctx_->last_residuals = rc == B200_OK ? residuals : nullptr;
   if (rc == B200_ERR_EVALUATION_FAILED) return false;
   return Check(rc, "b200_evaluate");
 }
@@ -147,7 +148,9 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
   o.q_tolerance = per_solve_options.q_tolerance;
   o.r_tolerance = per_solve_options.r_tolerance;
   b200_solver_summary s{};
-  if (b200_schur_solve(jac->handle(), b, per_solve_options.D, &o, x, &s) != B200_OK) {
+  // b is the residual vector of the last Evaluate in the LM loop: its device copy is still valid (b200ba.h)
+  const double* b_arg = (b == jac->context().last_residuals) ? nullptr : b;
+  if (b200_schur_solve(jac->handle(), b_arg, per_solve_options.D, &o, x, &s) != B200_OK) {
     summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
     summary.message = b200_last_error();
     return summary;

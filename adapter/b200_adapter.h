@@ -28,6 +28,9 @@ namespace ceres::internal {
 // Shared owner of the device problem; evaluator, Jacobian and linear solver all point at it.
 struct B200Context {
   b200_handle* handle = nullptr;
+  // Host vector the last Evaluate() filled with residuals: when the minimizer hands the same pointer to the linear
+  // solver (trust_region_minimizer.cc:399-402) the copy that is still in HBM is used instead of uploading it again.
+  const double* last_residuals = nullptr;
   ~B200Context() { b200_destroy(handle); }
 };
 
@@ -36,6 +39,11 @@ class B200Jacobian final : public BlockSparseMatrix {  // needs `final` dropped 
   B200Jacobian(CompressedRowBlockStructure* bs, std::shared_ptr<B200Context> ctx)
       : BlockSparseMatrix(bs), ctx_(std::move(ctx)) {}
   b200_handle* handle() const { return ctx_->handle; }
+  const B200Context& context() const { return *ctx_; }
+  // -(J step)'(r + J step / 2) in one pass, r = residuals of the last Evaluate (optional minimizer hunk, ceres_b200.patch)
+  bool ModelCostChange(const double* step, double* model_cost_change) const {
+    return b200_model_cost_change(ctx_->handle, step, model_cost_change) == B200_OK;
+  }
 
   // The four calls TrustRegionMinimizer / LevenbergMarquardtStrategy make on the Jacobian
   // (trust_region_minimizer.cc:269,277,431; levenberg_marquardt_strategy.cc:84).

@@ -72,7 +72,7 @@ class KernelStat(C.Structure):
 SYMBOLS = [
     "b200_nccl_unique_id", "b200_create", "b200_destroy", "b200_last_error", "b200_num_parameters",
     "b200_num_residuals", "b200_evaluate", "b200_plus", "b200_jacobian_squared_column_norm",
-    "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply",
+    "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply", "b200_model_cost_change",
     "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_jtj_multiply", "b200_solver_options_default",
     "b200_schur_solve", "b200_schur_init", "b200_schur_rhs", "b200_schur_ete_inverse", "b200_schur_multiply",
     "b200_schur_back_substitute", "b200_schur_jacobi_update", "b200_block_jacobi_update",
@@ -218,8 +218,14 @@ class Problem:
         o = options or self.solver_options()
         x = np.full(self.num_parameters, np.nan)
         s = SolverSummary()
-        _check(lib().b200_schur_solve(self.h, _d(_f64(b)), _d(_f64(D)), C.byref(o), _d(x), C.byref(s)))
+        bp = _d(_f64(b)) if b is not None else None  # None: the residuals of the last evaluate(), still in HBM
+        _check(lib().b200_schur_solve(self.h, bp, _d(_f64(D)), C.byref(o), _d(x), C.byref(s)))
         return x, s.num_iterations, s.termination_type
+
+    def model_cost_change(self, step):
+        out = C.c_double(0.0)
+        _check(lib().b200_model_cost_change(self.h, _d(_f64(step)), C.byref(out)))
+        return out.value
 
     def schur_init(self, b, D):
         _check(lib().b200_schur_init(self.h, _d(_f64(b)), _d(_f64(D))))

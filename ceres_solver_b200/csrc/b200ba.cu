@@ -188,7 +188,8 @@ struct b200_handle {
          *d_cand = nullptr, *d_y = nullptr;
   // pinned host staging for scalars
   double* h_scalars = nullptr;
-  CgState* h_cg = nullptr;
+  CgState* h_cg = nullptr;      // two pinned slots: the host polls one batch behind the launches
+  cudaEvent_t ev_cg[2] = {nullptr, nullptr};
   int* h_fail = nullptr;
   // v2 (warp-tile, shared-memory-privatised camera vector) path
   bool v2_ok = false;
@@ -199,9 +200,11 @@ struct b200_handle {
   int2* d_cta_big = nullptr;
   uint32_t* d_tile_meta = nullptr;
   bool mul_v4 = false, mul_v4_owned = false;
+  bool residuals_resident = false;  // d_residuals holds the residuals of the last b200_evaluate(..., residuals != NULL)
   bool pcg_ok = false;       // the whole PCG runs as one persistent cooperative kernel (pcg_kernel.cuh)
   int pcg_cams_per_cta = 0;
   double *d_qa = nullptr, *d_qb = nullptr, *d_pcg_red = nullptr;
+  double *d_pq_parts = nullptr, *d_seed_pq = nullptr;  // fused p.q: per-CTA partials of the product / of the vector kernel
   unsigned* d_pcg_barrier = nullptr;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
@@ -223,6 +226,7 @@ struct b200_handle {
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
   int cg_grid = 1;
+  int cg_cluster_cams = 0;   // > 0: cg_cluster_kernel with this many cameras per CTA replaces the cooperative kernel
   PinnedVec hv[12];           // host-boundary LM loop vectors
   // launch geometry
   int grid_tile[K_COUNT];
@@ -462,8 +466,8 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
         diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
       }));
     OK(launch(h, K_SCHUR_MUL, [&] {
-      if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
-      else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
+      if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag, nullptr);
+      else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag, nullptr);
       else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
       else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
     }));
@@ -578,11 +582,22 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     va.mode = mode;
     va.q = q;
     va.seed_target = seeded ? seed_target : nullptr;
+    if (h->cg_cluster_cams > 0)  // one 8-CTA cluster, cluster barriers instead of grid syncs
+      return launch(h, K_CG_VEC, [&] {
+        cg_cluster_kernel<<<kCgClusterSize, kCgClusterThreads, sizeof(double) * 9 * h->cg_cluster_cams, h->stream>>>(va, h->cg_cluster_cams);
+      });
     void* args[] = {&va};
     return launch(h, K_CG_VEC, [&] {
       cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
     });
   };
+  // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
+  const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && (h->num_big_tiles == 0 || h->big_folded) &&
+                       getenv("B200_NO_FUSED_PQ") == nullptr;
+  double* pq_parts = fuse_pq ? h->d_pq_parts : nullptr;
+  va.pq_parts = pq_parts;
+  va.num_pq_parts = fuse_pq ? h->v2.num_ctas : 0;
+  va.seed_pq = fuse_pq ? h->d_seed_pq : nullptr;
   auto product = [&](const double* vin, double* out) -> int {
     if (seeded) {
       // The handful of >32-row points runs on a side stream, concurrently with the warp-tile kernel (both only add
@@ -597,8 +612,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
-        else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
+        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done, pq_parts);
+        else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done, pq_parts);
         else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
@@ -670,14 +685,13 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   }
   OK(vec(CG_BEGIN, h->d_z, h->d_z));
   const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
-  // Termination is decided on the device; the host only polls the state every few iterations
-  // (kernels become no-ops once done is set), so there is no per-iteration synchronisation.
-  int check_every = h->profiling ? 1 : 2;  // (profiling: no launches after termination, they would skew the means)
-  bool done = false;
-  int it = 0;
+  // Termination is decided on the device; the host only polls the state every few iterations (kernels become
+  // no-ops once done is set), and it polls one batch BEHIND what it has already enqueued, so the GPU never drains
+  // while the host looks at the state: batch k+1 is in the queue before the host waits for the state after batch k.
   const int max_it = std::max(o->max_num_iterations, 1);
-  while (!done) {
-    for (int k = 0; k < check_every && it < max_it; ++k) {
+  int it = 0;
+  auto batch = [&](int count) -> int {
+    for (int k = 0; k < count && it < max_it; ++k) {
       ++it;
       // q aliases z exactly like the reference (conjugate_gradients_solver.h:193): z is dead once p is updated.
       OK(product(h->d_p, h->d_z));
@@ -689,10 +703,38 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         OK(vec(CG_NORMAL, h->d_z, h->d_z));
       }
     }
-    CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    done = h->h_cg->done != 0 || it >= max_it;
-    if (!h->profiling) check_every = std::min(check_every * 2, 8);
+    return B200_OK;
+  };
+  if (h->profiling) {
+    // instrumented runs poll after every iteration: no launches after termination, they would skew the per-kernel means
+    bool done = false;
+    while (!done) {
+      OK(batch(1));
+      CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      done = h->h_cg->done != 0 || it >= max_it;
+    }
+    return finish();
+  }
+  int check_every = 2;
+  int pending = 0;
+  OK(batch(check_every));
+  CU(cudaMemcpyAsync(h->h_cg + pending, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->ev_cg[pending], h->stream));
+  for (;;) {
+    const bool more = it < max_it;
+    if (more) {
+      check_every = std::min(check_every * 2, 8);
+      OK(batch(check_every));
+      CU(cudaMemcpyAsync(h->h_cg + (1 - pending), h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaEventRecord(h->ev_cg[1 - pending], h->stream));
+    }
+    CU(cudaEventSynchronize(h->ev_cg[pending]));
+    if (h->h_cg[pending].done != 0 || !more) {
+      if (pending != 0) h->h_cg[0] = h->h_cg[pending];
+      break;
+    }
+    pending = 1 - pending;
   }
   return finish();
 }
@@ -1079,7 +1121,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   OK(dev_alloc(&h->d_cand, h->np));
   OK(dev_alloc(&h->d_y, h->np));
   CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_scalars), 64 * sizeof(double)));
-  CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_cg), sizeof(CgState)));
+  CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_cg), 2 * sizeof(CgState)));
+  CU(cudaEventCreateWithFlags(&h->ev_cg[0], cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&h->ev_cg[1], cudaEventDisableTiming));
   CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_fail), 4 * sizeof(int)));
   CU(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_cam_idx, desc->cam_idx, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -1304,6 +1348,21 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     const int nblocks = (C + kCgCamsPerCta - 1) / kCgCamsPerCta;
     h->cg_grid = std::max(1, std::min(nblocks, per_sm * h->sm_count));
     OK(dev_alloc(&h->d_red, static_cast<size_t>(h->cg_grid) * 4));
+    OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(std::max(h->cg_grid, kCgClusterSize))));
+    {
+      const int cpc = (C + kCgClusterSize - 1) / kCgClusterSize;
+      const size_t need = sizeof(double) * 9 * static_cast<size_t>(cpc);
+      // Opt-in experiment (B200_CG_CLUSTER=1): measured slower than the 62-CTA cooperative kernel (18 vs 12 us per
+      // launch on Ladybug-1723 -- eight SMs serialise the L2 round trips that 62 SMs overlap).
+      if (need + 8192 <= prop.sharedMemPerBlockOptin && getenv("B200_CG_CLUSTER") != nullptr) {
+        // (function attributes are process-wide: raise to the device limit, never to this handle's need)
+        CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 4096));
+        h->cg_cluster_cams = cpc;
+      }
+    }
+    OK(dev_alloc(&h->d_pq_parts, static_cast<size_t>(prop.multiProcessorCount)));
+    CU(cudaMemsetAsync(h->d_seed_pq, 0, sizeof(double) * std::max(h->cg_grid, kCgClusterSize), h->stream));
+    CU(cudaMemsetAsync(h->d_pq_parts, 0, sizeof(double) * prop.multiProcessorCount, h->stream));
   }
 
   // Algorithmic (compulsory) bytes per launch, SURVEY §8d with this layout: J values 192 B/row + 4 B camera
@@ -1336,12 +1395,14 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
   if (h->h_cg) cudaFreeHost(h->h_cg);
+  for (cudaEvent_t e : h->ev_cg)
+    if (e != nullptr) cudaEventDestroy(e);
   if (h->h_fail) cudaFreeHost(h->h_fail);
   for (auto& ep : h->pending) {
     cudaEventDestroy(ep.a);
@@ -1371,7 +1432,10 @@ int b200_evaluate(b200_handle* h, const double* state, double* cost, double* res
   OK(h2d(h, h->d_state, state, sizeof(double) * h->np));
   OK(evaluate_dev(h, h->d_state, residuals != nullptr ? h->d_residuals : nullptr,
                   gradient != nullptr ? h->d_gradient : nullptr, want_jacobian != 0, nullptr, cost));
-  if (residuals != nullptr) OK(d2h(h, residuals, h->d_residuals, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+  if (residuals != nullptr) {
+    OK(d2h(h, residuals, h->d_residuals, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    h->residuals_resident = true;  // the copy in HBM stays valid until the next evaluation that asks for residuals
+  }
   if (gradient != nullptr) OK(d2h(h, gradient, h->d_gradient, sizeof(double) * h->np));
   return B200_OK;
 }
@@ -1410,6 +1474,22 @@ int b200_jacobian_right_multiply(b200_handle* h, const double* x, double* y) {
     jmul_kernel<<<h->grid_tile[K_JMUL], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_vp0, h->d_vr0);
   }));
   return d2h(h, y, h->d_vr0, sizeof(double) * nr);
+}
+
+int b200_model_cost_change(b200_handle* h, const double* step, double* model_cost_change) {
+  if (h == nullptr || step == nullptr || model_cost_change == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (!h->residuals_resident) return fail(B200_ERR_INVALID_ARGUMENT, "needs the residuals of a previous b200_evaluate");
+  CU(cudaSetDevice(h->device));
+  OK(h2d(h, h->d_vp0, step, sizeof(double) * h->np));
+  OK(launch(h, K_MODEL_COST, [&] {
+    model_cost_kernel<<<h->grid_tile[K_MODEL_COST], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_vp0, h->d_residuals, h->d_tile_partial);
+  }));
+  OK(launch(h, K_MISC, [&] { sum_kernel<<<1, kVecThreads, 0, h->stream>>>(h->num_tiles, h->d_tile_partial, h->d_scalars + 1); }));
+  OK(allreduce_sum(h, h->d_scalars + 1, 1));
+  CU(cudaMemcpyAsync(h->h_scalars + 1, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *model_cost_change = h->h_scalars[1];
+  return B200_OK;
 }
 
 int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y) {
@@ -1481,12 +1561,18 @@ int b200_jacobian_set_values(b200_handle* h, const double* values) {
 // ------------------------------------------------------------------------------------------------ LinearSolver
 int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b200_solver_options* opts, double* x,
                      b200_solver_summary* summary) {
-  if (h == nullptr || b == nullptr || opts == nullptr || x == nullptr || summary == nullptr)
+  if (h == nullptr || opts == nullptr || x == nullptr || summary == nullptr)
     return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (b == nullptr && !h->residuals_resident)
+    return fail(B200_ERR_INVALID_ARGUMENT, "b == NULL means the residuals of the last b200_evaluate, and there are none");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+  const double* d_b = h->d_residuals;
+  if (b != nullptr) {
+    OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    d_b = h->d_b;
+  }
   if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
-  OK(schur_solve_dev(h, h->d_b, D != nullptr ? h->d_D : nullptr, opts, h->d_y, summary));
+  OK(schur_solve_dev(h, d_b, D != nullptr ? h->d_D : nullptr, opts, h->d_y, summary));
   if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR)
     OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
   return B200_OK;
@@ -1673,7 +1759,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
       }
       for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
       for (int i = 0; i < np; ++i) sol[i] = std::numeric_limits<double>::quiet_NaN();
-      OK(b200_schur_solve(h, residuals.data(), lmD.data(), &so, sol.data(), &ls));
+      OK(b200_schur_solve(h, nullptr /* residuals of the last evaluate, still in HBM */, lmD.data(), &so, sol.data(), &ls));
       if (ls.termination_type != B200_LS_FAILURE && ls.termination_type != B200_LS_FATAL_ERROR) {
         for (int i = 0; i < np; ++i) step_finite = step_finite && std::isfinite(sol[i]);
         if (step_finite)
@@ -1695,11 +1781,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     double step_sq = 0.0, x_sq = 0.0;
     if (solver_ok) {
       if (host_boundary) {
-        std::fill(model_res.begin(), model_res.end(), 0.0);
-        OK(b200_jacobian_right_multiply(h, step.data(), model_res.data()));
-        double dot = 0.0;
-        for (size_t i = 0; i < nr; ++i) dot += model_res[i] * (residuals[i] + model_res[i] / 2.0);
-        model_cost_change = -dot;
+        OK(b200_model_cost_change(h, step.data(), &model_cost_change));
       } else {
         // step = -y, delta = step * scaling, candidate = x + delta and the norms, in one pass
         double red[3];

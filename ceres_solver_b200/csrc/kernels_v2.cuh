@@ -803,10 +803,12 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
   for (int s = 0; s < v.stages; ++s) flip ^= (((it - s + v.stages - 1) / v.stages) & 1u) << s;
 }
 
+// pq_part (may be null): the CTA also writes x . (its partial of y) there -- the p.q of the PCG without a pass over q
+// (the D_f^2 term is added by the vector kernel, which seeds y with it).
 template <bool kOwned>
 __global__ void __launch_bounds__(kV4MaxThreads, 1)
     schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
-                        const int* __restrict__ done_flag) {
+                        const int* __restrict__ done_flag, double* pq_part) {
   if (done_flag != nullptr && *done_flag != 0) return;
   const V4Ctx c = v4_ctx(v);
   v4_init(v, c);
@@ -821,7 +823,29 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
   uint32_t flip = 0;
   v4_tiles<kOwned>(v, ete_inv, c, flip);
   v4_big_points(v, c, ete_inv);
-  v2_epilogue(v, c.sy(), c.cr, y);
+  if (pq_part == nullptr || !v.direct) {
+    v2_epilogue(v, c.sy(), c.cr, y);
+    return;
+  }
+  // direct flush + x . partial
+  __shared__ double s_pq;
+  if (threadIdx.x == 0) s_pq = 0.0;
+  __syncthreads();
+  const int n = 9 * (c.cr.y - c.cr.x);
+  const double* sy = c.sy();
+  const double* sx = c.sx();
+  double pq = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double acc = sy[i];
+    for (int r = 1; r < v.replicas; ++r) acc += sy[r * c.sy_stride + i];
+    if (acc != 0.0) red_add(y + 9 * static_cast<size_t>(c.cr.x) + i, acc);
+    pq += sx[i] * acc;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) pq += __shfl_xor_sync(0xffffffffu, pq, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_pq, pq);
+  __syncthreads();
+  if (threadIdx.x == 0) pq_part[blockIdx.x] = s_pq;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -88,6 +88,10 @@ int b200_jacobian_squared_column_norm(b200_handle* h, double* x);            /* 
 int b200_jacobian_scale_columns(b200_handle* h, const double* scale);        /* :403-450 */
 int b200_jacobian_right_multiply(b200_handle* h, const double* x, double* y);/* y += J x,  :239-274 */
 int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y); /* y += J' x, :278-349 */
+/* The one use the minimizer has for J*step, fused: model_cost_change = -(J step)'(r + J step / 2) with r the residuals
+ * of the last b200_evaluate (still in HBM) -- trust_region_minimizer.cc:430-438 (ParallelSetZero +
+ * RightMultiplyAndAccumulate + Dot) in one pass over J, returning one scalar instead of the 2N-vector J*step. */
+int b200_model_cost_change(b200_handle* h, const double* step, double* model_cost_change);
 int b200_jacobian_get_values(b200_handle* h, double* values);                /* BlockSparseMatrix::values(), 24N */
 int b200_jacobian_set_values(b200_handle* h, const double* values);          /* mutable_values() */
 /* y = (J'J + diag(D)^2) x in one pass over J (D may be NULL).  The normal-equations product CGNR uses
@@ -110,6 +114,9 @@ typedef struct b200_solver_summary { /* LinearSolver::Summary, linear_solver.h:3
   int32_t termination_type;          /* B200_LS_* */
 } b200_solver_summary;
 void b200_solver_options_default(b200_solver_options* o);
+/* b == NULL: b is the residual vector the last b200_evaluate produced, which is still in HBM (the minimizer passes
+ * exactly that vector, trust_region_minimizer.cc:399-402 via levenberg_marquardt_strategy.cc:116; the adapter
+ * compares the pointer with the one it filled in Evaluate and skips the 16N-byte upload). */
 int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b200_solver_options* opts,
                      double* x, b200_solver_summary* summary);
 

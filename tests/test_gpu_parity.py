@@ -207,6 +207,25 @@ def test_schur_solve_matches_oracle(precond, c16_case, cs):
         assert relerr(x_o, x_exact) < 10 * tol
 
 
+def test_resident_residuals_and_fused_model_cost(c16_case, cs):
+    """b == NULL in b200_schur_solve and b200_model_cost_change use the residuals of the last evaluate (still in HBM):
+    same answers as the explicit host-vector forms (trust_region_minimizer.cc:399-402, :430-438)."""
+    case = c16_case
+    J, b, D = _scaled_system(case)   # evaluates: residuals b are resident on the device
+    o = case.gpu.solver_options(q_tolerance=1e-2, r_tolerance=-1.0)
+    x1, its1, term1 = case.gpu.schur_solve(b, D, o)
+    x0, its0, term0 = case.gpu.schur_solve(None, D, o)
+    assert (its0, term0) == (its1, term1)
+    assert relerr(x0, x1) < 1e-9
+    step = -x1
+    jr = J.right_multiply(step, nt=8)
+    expect = -float(np.dot(jr, b + jr / 2.0))
+    got = case.gpu.model_cost_change(step)
+    assert abs(got - expect) <= 1e-10 * abs(expect)
+    via_vector = case.gpu.right_multiply(step)
+    assert abs(got + float(np.dot(via_vector, b + via_vector / 2.0))) <= 1e-10 * abs(expect)
+
+
 def test_schur_solve_max_iterations(c16_case, cs):
     case = c16_case
     J, b, D = _scaled_system(case)
