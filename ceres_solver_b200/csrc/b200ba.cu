@@ -32,6 +32,7 @@
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
 #include "pcg_kernel.cuh"
+#include "pcg_split.cuh"
 
 using namespace b200;
 
@@ -204,6 +205,11 @@ struct b200_handle {
   bool pcg_ok = false;       // the whole PCG runs as one persistent cooperative kernel (pcg_kernel.cuh)
   int pcg_cams_per_cta = 0;
   double *d_qa = nullptr, *d_qb = nullptr, *d_pcg_red = nullptr;
+  bool split_ok = false;      // split-phase PCG (pcg_split.cuh): no grid-wide barrier anywhere in the iteration
+  int2* d_cta_own = nullptr;
+  CgState* d_cg3 = nullptr;   // [3] ping-pong slots + final summary
+  double* d_split_red = nullptr;
+  int split_grid = 0;
   double *d_pq_parts = nullptr, *d_seed_pq = nullptr;  // fused p.q: per-CTA partials of the product / of the vector kernel
   unsigned* d_pcg_barrier = nullptr;
   WarpTile* d_wtiles = nullptr;
@@ -680,6 +686,108 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         fclose(f);
       }
       cudaFree(d_trace);
+    }
+    return finish();
+  }
+  if (h->split_ok) {
+    // split-phase PCG: vector kernel (alpha, x, r, z, partial sums) and product kernel (tests, beta, p, S0 p, p.q)
+    // alternate; neither needs a grid-wide barrier (pcg_split.cuh)
+    const int max_it = std::max(o->max_num_iterations, 1);
+    const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
+    if (h->d_pq_parts == nullptr) return fail(B200_ERR_CUDA, "split PCG buffers missing");
+    CgSplitArgs ca{};
+    ca.prm = prm;
+    ca.prm.max_iterations = max_it;
+    ca.C = h->C;
+    ca.st = h->d_cg3;
+    ca.Df = Df;
+    ca.precond = precond;
+    ca.minv = h->d_minv;
+    ca.rhs = h->d_rhs;
+    ca.x = h->d_sol;
+    ca.r = h->d_r;
+    ca.z = h->d_z;
+    ca.p = h->d_p;
+    ca.pq_parts = h->d_pq_parts;
+    ca.num_pq_parts = h->v2.num_ctas;
+    ca.red = h->d_split_red;
+    PcgLink L{};
+    L.st = h->d_cg3;
+    L.prm = ca.prm;
+    L.red = h->d_split_red;
+    L.red_n = h->split_grid;
+    L.z = h->d_z;
+    L.p = h->d_p;
+    L.xvec = h->d_sol;
+    L.Df = Df;
+    L.cta_own = h->d_cta_own;
+    L.pq_parts = h->d_pq_parts;
+    int slot = 0;
+    auto vecs = [&](int mode, const double* q, double* zero_a, double* zero_b) -> int {
+      ca.mode = mode;
+      ca.slot = slot;
+      ca.q = q;
+      ca.zero_a = zero_a;
+      ca.zero_b = zero_b;
+      return launch(h, K_CG_VEC, [&] { cg_split_kernel<<<h->split_grid, kSplitThreads, 0, h->stream>>>(ca); });
+    };
+    auto prod = [&](int mode, double* out) -> int {
+      L.mode = mode;
+      L.slot = slot;
+      OK(launch(h, K_SCHUR_MUL, [&] {
+        if (h->mul_v4_owned) schur_mul_v4_pcg_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, L, out);
+        else schur_mul_v4_pcg_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, L, out);
+      }));
+      if (mode != PM_RESET_X) slot = 1 - slot;
+      return B200_OK;
+    };
+    double* qbuf[2] = {h->d_qa, h->d_qb};
+    OK(vecs(CA_BEGIN, nullptr, h->d_qa, h->d_qb));
+    OK(prod(PM_FIRST, qbuf[1]));          // tests of the start state, p = z, S0 p of iteration 1
+    int it = 0;
+    auto batch = [&](int count) -> int {
+      for (int k = 0; k < count && it < max_it; ++k) {
+        ++it;
+        if (it % reset == 0) {
+          OK(vecs(CA_RESET_FIRST, nullptr, h->d_tmp, nullptr));
+          OK(prod(PM_RESET_X, h->d_tmp));
+          OK(vecs(CA_RESET_SECOND, h->d_tmp, qbuf[(it + 1) & 1], nullptr));
+        } else {
+          OK(vecs(CA_NORMAL, qbuf[it & 1], qbuf[(it + 1) & 1], nullptr));
+        }
+        OK(prod(PM_NORMAL, qbuf[(it + 1) & 1]));   // tests of iteration `it`, then S0 p of iteration it + 1
+      }
+      return B200_OK;
+    };
+    const CgState* d_final = h->d_cg3 + 2;
+    if (h->profiling) {
+      bool done = false;
+      while (!done) {
+        OK(batch(1));
+        CU(cudaMemcpyAsync(h->h_cg, d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        done = h->h_cg->done != 0 || it >= max_it;
+      }
+      return finish();
+    }
+    int check_every = 2, pending = 0;
+    OK(batch(check_every));
+    CU(cudaMemcpyAsync(h->h_cg + pending, d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaEventRecord(h->ev_cg[pending], h->stream));
+    for (;;) {
+      const bool more = it < max_it;
+      if (more) {
+        check_every = std::min(check_every * 2, 8);
+        OK(batch(check_every));
+        CU(cudaMemcpyAsync(h->h_cg + (1 - pending), d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev_cg[1 - pending], h->stream));
+      }
+      CU(cudaEventSynchronize(h->ev_cg[pending]));
+      if (h->h_cg[pending].done != 0 || !more) {
+        if (pending != 0) h->h_cg[0] = h->h_cg[pending];
+        break;
+      }
+      pending = 1 - pending;
     }
     return finish();
   }
@@ -1264,6 +1372,41 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     h->v2_ok = true;
+    // Opt-in experiment (B200_SPLIT_PCG=1): split-phase PCG without any grid-wide barrier (pcg_split.cuh).  Measured
+    // within +-1.5 % of the default on the large problems and 13 % slower on C16 (the tests move into the product's
+    // prologue): the iteration is bound by its two kernel boundaries, not by the grid sync of the vector kernel.
+    if (h->mul_v4 && h->world == 1 && h->big_folded && h->v2.direct && getenv("B200_SPLIT_PCG") != nullptr) {
+      // camera ownership for the D_f^2 p^2 term of p.q: the first CTA whose range contains the camera; every camera
+      // must be covered by the (sorted) ranges
+      std::vector<int2> own(num_ctas_v2, make_int2(0, 0));
+      int covered = 0;
+      bool gapless = true;
+      for (int b = 0; b < num_ctas_v2; ++b) {
+        if (cta_cam[b].y <= cta_cam[b].x) continue;
+        if (cta_cam[b].x > covered) gapless = false;
+        const int lo = std::max(cta_cam[b].x, covered);
+        if (lo < cta_cam[b].y) {
+          own[b] = make_int2(lo, cta_cam[b].y);
+          covered = cta_cam[b].y;
+        }
+      }
+      if (gapless && covered == C) {
+        OK(dev_alloc(&h->d_cta_own, own.size()));
+        CU(cudaMemcpyAsync(h->d_cta_own, own.data(), own.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+        h->split_grid = (C + kSplitCamsPerCta - 1) / kSplitCamsPerCta;
+        OK(dev_alloc(&h->d_split_red, static_cast<size_t>(h->split_grid) * 4));
+        OK(dev_alloc(&h->d_cg3, 3));
+        CU(cudaMemsetAsync(h->d_cg3, 0, 3 * sizeof(CgState), h->stream));
+        if (h->d_qa == nullptr) {
+          OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
+          OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
+        }
+        CU(cudaFuncSetAttribute(schur_mul_v4_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_mul_v4_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaStreamSynchronize(h->stream));
+        h->split_ok = true;
+      }
+    }
     // Opt-in experiment (B200_PCG_PERSISTENT=1): the whole PCG as one persistent kernel.  Measured SLOWER than one
     // product launch + one vector launch per iteration (59 vs 43 us per iteration on Ladybug-1723: software grid
     // barriers and the serial vector phases on 148 fat CTAs cost more than two kernel boundaries; see
@@ -1274,8 +1417,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       if (h->mul_v4_owned) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<true>, 32 * h->v2_mul.warps, h->mul_smem));
       else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, 32 * h->v2_mul.warps, h->mul_smem));
       if (9 * cpc <= 32 * h->v2_mul.warps && per_sm >= 1 && prop.cooperativeLaunch) {
-        OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
-        OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
+        if (h->d_qa == nullptr) {
+          OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
+          OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
+        }
         OK(dev_alloc(&h->d_pcg_red, static_cast<size_t>(num_ctas_v2) * 8));
         OK(dev_alloc(&h->d_pcg_barrier, 4));
         CU(cudaMemsetAsync(h->d_pcg_red, 0, sizeof(double) * num_ctas_v2 * 8, h->stream));
@@ -1326,10 +1471,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
 
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
-            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d\n",
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d split=%d\n",
             C, P, N, wtiles.size(), big_tiles.size(), max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
             h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
-            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->pcg_ok ? 1 : 0);
+            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->pcg_ok ? 1 : 0, h->split_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -1395,7 +1540,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

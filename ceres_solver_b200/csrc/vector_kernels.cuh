@@ -13,7 +13,7 @@ namespace b200 {
 constexpr int kVecThreads = 1024;
 
 struct CgState {
-  double rho, last_rho, Q0, norm_rhs, tol_r, norm_r, alpha, pq;
+  double rho, last_rho, Q0, norm_rhs, tol_r, norm_r, alpha, pq, beta;
   int iteration;    // summary.num_iterations
   int done;         // 1 once a termination criterion fired
   int termination;  // B200_LS_*
