@@ -1897,18 +1897,37 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     so.r_tolerance = -1.0;
     b200_solver_summary ls{};
     bool step_finite = true;
+    double host_x_sq = 0.0, host_step_sq = 0.0;
     if (host_boundary) {
+      // (the host-side vector passes mirror what the reference minimizer does on its Eigen vectors; adjacent ones are
+      // fused so that each array is streamed once)
       if (!reuse_diagonal) {
         OK(b200_jacobian_squared_column_norm(h, diagonal.data()));
-        for (int i = 0; i < np; ++i) diagonal[i] = std::min(std::max(diagonal[i], opt->min_lm_diagonal), opt->max_lm_diagonal);
+        for (int i = 0; i < np; ++i) {
+          diagonal[i] = std::min(std::max(diagonal[i], opt->min_lm_diagonal), opt->max_lm_diagonal);
+          lmD[i] = std::sqrt(diagonal[i] / radius);
+        }
+      } else {
+        for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
       }
-      for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
-      for (int i = 0; i < np; ++i) sol[i] = std::numeric_limits<double>::quiet_NaN();
+      std::fill(sol.begin(), sol.end(), std::numeric_limits<double>::quiet_NaN());  // levenberg_marquardt_strategy.cc:108
       OK(b200_schur_solve(h, nullptr /* residuals of the last evaluate, still in HBM */, lmD.data(), &so, sol.data(), &ls));
       if (ls.termination_type != B200_LS_FAILURE && ls.termination_type != B200_LS_FATAL_ERROR) {
-        for (int i = 0; i < np; ++i) step_finite = step_finite && std::isfinite(sol[i]);
-        if (step_finite)
-          for (int i = 0; i < np; ++i) step[i] = -sol[i];
+        // step = -sol, delta = step * scaling, candidate = x + delta (Evaluator::Plus on Euclidean blocks) and the two
+        // norms the minimizer needs, in one pass
+        double acc_x = 0.0, acc_s = 0.0, bad = 0.0;
+        for (int i = 0; i < np; ++i) {
+          const double si = -sol[i];
+          step[i] = si;
+          const double ci = x[i] + si * scaling[i];
+          cand[i] = ci;
+          acc_x += x[i] * x[i];
+          acc_s += (x[i] - ci) * (x[i] - ci);
+          bad += (si - si);  // NaN/Inf - itself is NaN, finite - itself is 0
+        }
+        step_finite = (bad == 0.0);
+        host_x_sq = acc_x;
+        host_step_sq = acc_s;
       }
     } else {
       if (!reuse_diagonal && !sqnorm_fresh) OK(sqnorm_dev(h, h->d_sqnorm));
@@ -1973,13 +1992,9 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     // ---- ComputeCandidatePointAndEvaluateCost
     int rc;
     if (host_boundary) {
-      for (int i = 0; i < np; ++i) delta[i] = step[i] * scaling[i];
-      OK(b200_plus(h, x.data(), delta.data(), cand.data()));
       rc = b200_evaluate(h, cand.data(), &candidate_cost, nullptr, nullptr, 0);
-      for (int i = 0; i < np; ++i) {
-        x_sq += x[i] * x[i];
-        step_sq += (x[i] - cand[i]) * (x[i] - cand[i]);
-      }
+      x_sq = host_x_sq;
+      step_sq = host_step_sq;
     } else {
       rc = evaluate_dev(h, h->d_cand, nullptr, nullptr, false, nullptr, &candidate_cost);
     }
