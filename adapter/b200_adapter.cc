@@ -137,6 +137,7 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
     case IDENTITY: o.preconditioner_type = B200_PRECOND_IDENTITY; break;
     case JACOBI: o.preconditioner_type = B200_PRECOND_JACOBI; break;
     case SCHUR_JACOBI: o.preconditioner_type = B200_PRECOND_SCHUR_JACOBI; break;
+    case SCHUR_POWER_SERIES_EXPANSION: o.preconditioner_type = B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION; break;
     default:
       summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
       summary.message = "Preconditioner not implemented on the B200 path.";
@@ -145,6 +146,9 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
   o.min_num_iterations = options_.min_num_iterations;
   o.max_num_iterations = options_.max_num_iterations;
   o.residual_reset_period = options_.residual_reset_period;
+  o.max_num_spse_iterations = options_.max_num_spse_iterations;
+  o.use_spse_initialization = options_.use_spse_initialization ? 1 : 0;
+  o.spse_tolerance = options_.spse_tolerance;
   o.q_tolerance = per_solve_options.q_tolerance;
   o.r_tolerance = per_solve_options.r_tolerance;
   b200_solver_summary s{};

@@ -18,7 +18,7 @@ _ip = C.POINTER(C.c_int32)
 OK = 0
 ERR_EVALUATION_FAILED = -3
 LS_SUCCESS, LS_NO_CONVERGENCE, LS_FAILURE, LS_FATAL_ERROR = 0, 1, 2, 3
-PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_SCHUR_JACOBI = 0, 1, 2
+PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_SCHUR_JACOBI, PRECOND_SCHUR_POWER_SERIES_EXPANSION = 0, 1, 2, 3
 LOSS_TRIVIAL, LOSS_HUBER = 0, 1
 
 
@@ -38,7 +38,9 @@ class BaDesc(C.Structure):
 class SolverOptions(C.Structure):
     _fields_ = [("preconditioner_type", C.c_int32), ("min_num_iterations", C.c_int32),
                 ("max_num_iterations", C.c_int32), ("residual_reset_period", C.c_int32),
-                ("q_tolerance", C.c_double), ("r_tolerance", C.c_double)]
+                ("q_tolerance", C.c_double), ("r_tolerance", C.c_double),
+                ("max_num_spse_iterations", C.c_int32), ("use_spse_initialization", C.c_int32),
+                ("spse_tolerance", C.c_double)]
 
 
 class SolverSummary(C.Structure):

@@ -33,6 +33,7 @@
 #include "cg_kernel.cuh"
 #include "pcg_kernel.cuh"
 #include "pcg_split.cuh"
+#include "spse_kernels.cuh"
 
 using namespace b200;
 
@@ -205,6 +206,7 @@ struct b200_handle {
   bool pcg_ok = false;       // the whole PCG runs as one persistent cooperative kernel (pcg_kernel.cuh)
   int pcg_cams_per_cta = 0;
   double *d_qa = nullptr, *d_qb = nullptr, *d_pcg_red = nullptr;
+  double *d_ftf_inv = nullptr, *d_spse[3] = {nullptr, nullptr, nullptr};  // general-preconditioner PCG (SPSE)
   bool split_ok = false;      // split-phase PCG (pcg_split.cuh): no grid-wide barrier anywhere in the iteration
   int2* d_cta_own = nullptr;
   CgState* d_cg3 = nullptr;   // [3] ping-pong slots + final summary
@@ -542,11 +544,15 @@ int precond_update_dev(b200_handle* h, int type) {
   });
 }
 
+int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks);
+int pcg_general_dev(b200_handle* h, const b200_solver_options* o);
+
 // IterativeSchurComplementSolver::SolveImpl on device pointers.  d_x: [3P+9C] output.
 int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const b200_solver_options* o, double* d_x,
                     b200_solver_summary* summary) {
   OK(schur_init_dev(h, d_b, d_D));
-  OK(precond_update_dev(h, o->preconditioner_type));
+  const bool general = o->preconditioner_type == B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION || o->use_spse_initialization != 0;
+  if (!general) OK(precond_update_dev(h, o->preconditioner_type));
   const int n = 9 * h->C;
   CgParams prm{};
   prm.n = n;
@@ -687,6 +693,11 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       }
       cudaFree(d_trace);
     }
+    return finish();
+  }
+  if (general) {
+    // power-series preconditioner / initial guess -> the general-preconditioner PCG (host-side scalars)
+    OK(pcg_general_dev(h, o));
     return finish();
   }
   if (h->split_ok) {
@@ -847,7 +858,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   return finish();
 }
 
-int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks = false) {
+int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks) {
   OK(launch(h, K_LM_VEC, [&] { reduce_final_kernel<<<1, 32, 0, h->stream>>>(blocks, slots, op_mask, h->d_partial, h->d_scalars + 8); }));
 #ifdef B200_WITH_NCCL
   if (across_ranks && h->world > 1) {
@@ -866,6 +877,161 @@ int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, dou
   return B200_OK;
 }
 
+// ConjugateGradientsSolver (conjugate_gradients_solver.h:109-306) with an arbitrary preconditioner and initial guess, for
+// the configurations the fused PCG does not cover: SCHUR_POWER_SERIES_EXPANSION and use_spse_initialization
+// (iterative_schur_complement_solver.cc:100-111, :178-186).  Vectors on the device, scalars on the host.
+// Result in h->h_cg[0] {iteration, termination, norm_r}; the solution in h->d_sol.
+int pcg_general_dev(b200_handle* h, const b200_solver_options* o) {
+  const int n = 9 * h->C;
+  const int g = std::min(kRedBlocks, flat_grid(h, n, 256));
+  const int type = o->preconditioner_type;
+  if (type < B200_PRECOND_IDENTITY || type > B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION)
+    return fail(B200_ERR_INVALID_ARGUMENT, "unknown preconditioner type %d", type);
+  const bool need_ftf = type == B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION || o->use_spse_initialization != 0;
+  if (h->d_ftf_inv == nullptr) {
+    OK(dev_alloc(&h->d_ftf_inv, 81 * static_cast<size_t>(h->C)));
+    for (auto& b : h->d_spse) OK(dev_alloc(&b, static_cast<size_t>(n)));
+  }
+  if (need_ftf) {  // block_diagonal_FtF_inverse (implicit_schur_complement.cc:61-64, :90-95)
+    OK(precond_update_dev(h, B200_PRECOND_JACOBI));
+    CU(cudaMemcpyAsync(h->d_ftf_inv, h->d_minv, sizeof(double) * 81 * h->C, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (type == B200_PRECOND_JACOBI || type == B200_PRECOND_SCHUR_JACOBI) OK(precond_update_dev(h, type));
+
+  double *x = h->d_sol, *r = h->d_r, *z = h->d_z, *p = h->d_p, *tmp = h->d_tmp;
+  const double* rhs = h->d_rhs;
+  auto dots = [&](const double* a, const double* b, const double* c, const double* d, double* out2) -> int {
+    OK(launch(h, K_CG_VEC, [&] { dot2_kernel<<<g, 256, 0, h->stream>>>(n, a, b, c, d, h->d_partial); }));
+    return reduce_partials(h, g, 2, 0u, out2, false);
+  };
+  // y = power series approximation of S^-1 x   (power_series_expansion_preconditioner.cc:57-82)
+  auto spse = [&](const double* xin, double* y, int max_terms, double tol) -> int {
+    double *prev = h->d_spse[0], *term = h->d_spse[1], *t = h->d_spse[2];
+    OK(launch(h, K_CG_VEC, [&] { block_apply_kernel<<<g, 256, 0, h->stream>>>(n, h->d_ftf_inv, xin, y); }));
+    CU(cudaMemcpyAsync(prev, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    double thr = 0.0;
+    if (tol > 0.0) {
+      double d2[2];
+      OK(dots(y, y, nullptr, nullptr, d2));
+      thr = tol * std::sqrt(d2[0]);
+    }
+    for (int i = 1;; ++i) {
+      OK(schur_mul_dev(h, prev, t, nullptr));   // (F'F + D^2) prev - F'E P E'F prev
+      OK(launch(h, K_CG_VEC, [&] { spse_term_kernel<<<g, 256, 0, h->stream>>>(n, h->d_ftf_inv, prev, t, term, y, h->d_partial); }));
+      if (i >= max_terms) break;
+      if (tol > 0.0) {
+        double sq[1];
+        OK(reduce_partials(h, g, 1, 0u, sq, false));
+        if (std::sqrt(sq[0]) < thr) break;
+      }
+      std::swap(prev, term);
+    }
+    return B200_OK;
+  };
+  auto precondition = [&](const double* rin, double* zout) -> int {
+    switch (type) {
+      case B200_PRECOND_IDENTITY:
+        CU(cudaMemcpyAsync(zout, rin, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+        return B200_OK;
+      case B200_PRECOND_JACOBI:
+      case B200_PRECOND_SCHUR_JACOBI:
+        return launch(h, K_CG_VEC, [&] { block_apply_kernel<<<g, 256, 0, h->stream>>>(n, h->d_minv, rin, zout); });
+      default:  // tolerance 0 keeps the preconditioner fixed during the iterations (iterative_schur_complement_solver.cc:179-185)
+        return spse(rin, zout, std::max(o->max_num_spse_iterations, 1), 0.0);
+    }
+  };
+  CgState* st = h->h_cg;
+  std::memset(st, 0, sizeof(CgState));
+  st->done = 1;
+  st->termination = B200_LS_NO_CONVERGENCE;
+  st->iteration = 0;
+  auto is_zero_or_inf = [](double v) { return v == 0.0 || std::isinf(v); };
+
+  // initial guess
+  CU(cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
+  if (o->use_spse_initialization != 0) OK(spse(rhs, x, std::max(o->max_num_spse_iterations, 1), o->spse_tolerance));
+
+  double d2[2];
+  OK(dots(rhs, rhs, nullptr, nullptr, d2));
+  const double norm_rhs = std::sqrt(d2[0]);
+  if (norm_rhs == 0.0) {
+    CU(cudaMemsetAsync(x, 0, sizeof(double) * n, h->stream));
+    st->termination = B200_LS_SUCCESS;
+    return B200_OK;
+  }
+  const double tol_r = o->r_tolerance * norm_rhs;
+  // r = rhs - S x ; Q0 = -x.(rhs + r)
+  OK(schur_mul_dev(h, x, tmp, nullptr));
+  OK(launch(h, K_CG_VEC, [&] { cgg_update_kernel<<<g, 256, 0, h->stream>>>(n, 1, 0.0, nullptr, tmp, rhs, x, r, h->d_partial); }));
+  OK(reduce_partials(h, g, 2, 0u, d2, false));
+  double norm_r = std::sqrt(d2[1]);
+  st->norm_r = norm_r;
+  if (o->min_num_iterations == 0 && norm_r <= tol_r) {
+    st->termination = B200_LS_SUCCESS;
+    return B200_OK;
+  }
+  double rho = 1.0, Q0 = -d2[0];
+  const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
+  const int max_it = std::max(o->max_num_iterations, 1);
+  for (int it = 1;; ++it) {
+    st->iteration = it;
+    OK(precondition(r, z));
+    const double last_rho = rho;
+    OK(dots(r, z, nullptr, nullptr, d2));
+    rho = d2[0];
+    if (is_zero_or_inf(rho) || std::isnan(rho)) {
+      st->termination = B200_LS_FAILURE;
+      break;
+    }
+    if (it == 1) {
+      CU(cudaMemcpyAsync(p, z, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
+      const double beta = rho / last_rho;
+      if (is_zero_or_inf(beta)) {
+        st->termination = B200_LS_FAILURE;
+        break;
+      }
+      OK(launch(h, K_CG_VEC, [&] { axpby_kernel<<<g, 256, 0, h->stream>>>(n, 1.0, z, beta, p, p); }));
+    }
+    double* q = z;  // conjugate_gradients_solver.h:193
+    OK(schur_mul_dev(h, p, q, nullptr));
+    OK(dots(p, q, nullptr, nullptr, d2));
+    const double pq = d2[0];
+    if (!(pq > 0.0) || std::isinf(pq)) {
+      st->termination = std::isnan(pq) ? B200_LS_FAILURE : B200_LS_NO_CONVERGENCE;
+      break;
+    }
+    const double alpha = rho / pq;
+    if (std::isinf(alpha)) {
+      st->termination = B200_LS_FAILURE;
+      break;
+    }
+    if (it % reset == 0) {
+      OK(launch(h, K_CG_VEC, [&] { axpby_kernel<<<g, 256, 0, h->stream>>>(n, 1.0, x, alpha, p, x); }));
+      OK(schur_mul_dev(h, x, tmp, nullptr));
+      OK(launch(h, K_CG_VEC, [&] { cgg_update_kernel<<<g, 256, 0, h->stream>>>(n, 1, 0.0, nullptr, tmp, rhs, x, r, h->d_partial); }));
+    } else {
+      OK(launch(h, K_CG_VEC, [&] { cgg_update_kernel<<<g, 256, 0, h->stream>>>(n, 0, alpha, p, q, rhs, x, r, h->d_partial); }));
+    }
+    OK(reduce_partials(h, g, 2, 0u, d2, false));
+    const double Q1 = -d2[0];
+    const double zeta = it * (Q1 - Q0) / Q1;
+    norm_r = std::sqrt(d2[1]);
+    st->norm_r = norm_r;
+    if (zeta < o->q_tolerance && it >= o->min_num_iterations) {
+      st->termination = B200_LS_SUCCESS;
+      break;
+    }
+    Q0 = Q1;
+    if (norm_r <= tol_r && it >= o->min_num_iterations) {
+      st->termination = B200_LS_SUCCESS;
+      break;
+    }
+    if (it >= max_it) break;
+  }
+  return B200_OK;
+}
+
 // Reduction over a [points | cameras] vector when the points are sharded across ranks and the cameras are
 // replicated: the point range is reduced locally and combined across ranks, the camera range is counted once.
 // run(offset, count) must launch the partial-producing kernel on that sub-range with `grid` blocks.
@@ -874,13 +1040,13 @@ int sharded_reduce(b200_handle* h, int grid, int slots, unsigned op_mask, double
   const int nP = 3 * h->P, nC = 9 * h->C;
   if (h->world == 1) {
     OK(run(0, nP + nC));
-    return reduce_partials(h, grid, slots, op_mask, out);
+    return reduce_partials(h, grid, slots, op_mask, out, false);
   }
   double pt[8], cam[8];
   OK(run(0, nP));
   OK(reduce_partials(h, grid, slots, op_mask, pt, true));
   OK(run(nP, nC));
-  OK(reduce_partials(h, grid, slots, op_mask, cam));
+  OK(reduce_partials(h, grid, slots, op_mask, cam, false));
   for (int i = 0; i < slots; ++i) out[i] = ((op_mask >> i) & 1u) ? std::max(pt[i], cam[i]) : pt[i] + cam[i];
   return B200_OK;
 }
@@ -914,6 +1080,9 @@ void b200_solver_options_default(b200_solver_options* o) {
   o->residual_reset_period = 10;
   o->q_tolerance = 0.0;
   o->r_tolerance = 0.0;
+  o->max_num_spse_iterations = 5;   // linear_solver.h:172
+  o->use_spse_initialization = 0;   // :177
+  o->spse_tolerance = 0.1;          // :183
 }
 
 void b200_lm_options_default(b200_lm_options* o) {
@@ -1540,7 +1709,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

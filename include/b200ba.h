@@ -41,8 +41,13 @@ enum {
 
 /* LinearSolverTerminationType, internal/ceres/linear_solver.h:58-74 (same numeric order). */
 enum { B200_LS_SUCCESS = 0, B200_LS_NO_CONVERGENCE = 1, B200_LS_FAILURE = 2, B200_LS_FATAL_ERROR = 3 };
-/* PreconditionerType subset valid for ITERATIVE_SCHUR here (include/ceres/types.h). */
-enum { B200_PRECOND_IDENTITY = 0, B200_PRECOND_JACOBI = 1, B200_PRECOND_SCHUR_JACOBI = 2 };
+/* PreconditionerType subset valid for ITERATIVE_SCHUR here (include/ceres/types.h:93-119, same numeric order). */
+enum {
+  B200_PRECOND_IDENTITY = 0,
+  B200_PRECOND_JACOBI = 1,
+  B200_PRECOND_SCHUR_JACOBI = 2,
+  B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION = 3 /* power_series_expansion_preconditioner.cc:57-82 */
+};
 enum { B200_LOSS_TRIVIAL = 0, B200_LOSS_HUBER = 1 };
 
 /* Problem structure = what the adapters read off the reduced ceres::internal::Program
@@ -107,6 +112,10 @@ typedef struct b200_solver_options { /* LinearSolver::Options + PerSolveOptions,
   int32_t residual_reset_period;     /* linear_solver.h:211 (10) */
   double q_tolerance;                /* PerSolveOptions::q_tolerance (eta) */
   double r_tolerance;                /* PerSolveOptions::r_tolerance (-1 from LM) */
+  int32_t max_num_spse_iterations;   /* linear_solver.h:172 (5): terms of the power series */
+  int32_t use_spse_initialization;   /* :177 (0): start the PCG from the power series applied to the rhs
+                                        (iterative_schur_complement_solver.cc:100-111) */
+  double spse_tolerance;             /* :183 (0.1): early stop of that initialisation */
 } b200_solver_options;
 typedef struct b200_solver_summary { /* LinearSolver::Summary, linear_solver.h:320-326 */
   double residual_norm;

@@ -430,6 +430,7 @@ struct SolveOptions {
   int jacobi_scaling = 1;
   int max_num_consecutive_invalid_steps = 5;
   int num_threads = 1;
+  int use_spse_initialization = 0;          // solver.h:612 (max_num_spse_iterations 5, spse_tolerance 0.1: :607, :618)
 };
 
 struct IterationRecord {
@@ -463,6 +464,7 @@ inline int Minimize(BaProgram* program, const SolveOptions& opt, double* state_i
     IterativeSchurOptions so;
     so.num_eliminate_blocks = program->P;
     so.preconditioner_type = opt.preconditioner;
+    so.use_spse_initialization = opt.use_spse_initialization != 0;
     so.min_num_iterations = opt.min_linear_solver_iterations;
     so.max_num_iterations = opt.max_linear_solver_iterations;
     so.num_threads = nt;

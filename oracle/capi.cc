@@ -155,6 +155,10 @@ void orc_isc_init(void* s, const double* D, const double* b) { ORC_ISC_CALL(s, i
 void orc_isc_right_multiply(void* s, const double* x, double* y) { ORC_ISC_CALL(s, isc.RightMultiplyAndAccumulate(x, y)); }
 void orc_isc_rhs(void* s, double* out) { ORC_ISC_CALL(s, std::memcpy(out, isc.rhs.data(), sizeof(double) * isc.rhs.size())); }
 void orc_isc_back_substitute(void* s, const double* x, double* y) { ORC_ISC_CALL(s, isc.BackSubstitute(x, y)); }
+// y = power series approximation of S^-1 x (needs want_ftf at creation)
+void orc_isc_power_series(void* s, int max_num_spse_iterations, double spse_tolerance, const double* x, double* y) {
+  ORC_ISC_CALL(s, PowerSeriesExpansion(&isc, max_num_spse_iterations, spse_tolerance, x, y));
+}
 int orc_isc_ete_inverse(void* s, double* out) {
   int n = 0;
   ORC_ISC_CALL(s, { n = static_cast<int>(isc.ete_inv.values.size()); if (out) std::memcpy(out, isc.ete_inv.values.data(), sizeof(double) * n); });
@@ -197,9 +201,20 @@ void orc_schur_back_substitute(void* h, int num_elim, const double* b, const dou
 
 // ------------------------------------------------------------------ linear solvers
 // solver: 0 = ITERATIVE_SCHUR, 1 = DENSE_SCHUR. out_summary = {num_iterations, termination_type}.
+void orc_linear_solve_spse(void* h, int num_elim, int solver, int preconditioner, int min_iter, int max_iter,
+                           int residual_reset_period, double q_tolerance, double r_tolerance, const double* b,
+                           const double* D, double* x, int* out_summary, int nt, int force_dynamic,
+                           int max_num_spse_iterations, int use_spse_initialization, double spse_tolerance);
 void orc_linear_solve(void* h, int num_elim, int solver, int preconditioner, int min_iter, int max_iter,
                       int residual_reset_period, double q_tolerance, double r_tolerance, const double* b,
                       const double* D, double* x, int* out_summary, int nt, int force_dynamic) {
+  orc_linear_solve_spse(h, num_elim, solver, preconditioner, min_iter, max_iter, residual_reset_period, q_tolerance,
+                        r_tolerance, b, D, x, out_summary, nt, force_dynamic, 5, 0, 0.1);
+}
+void orc_linear_solve_spse(void* h, int num_elim, int solver, int preconditioner, int min_iter, int max_iter,
+                           int residual_reset_period, double q_tolerance, double r_tolerance, const double* b,
+                           const double* D, double* x, int* out_summary, int nt, int force_dynamic,
+                           int max_num_spse_iterations, int use_spse_initialization, double spse_tolerance) {
   auto& A = *static_cast<BlockSparseMatrix*>(h);
   IterativeSchurOptions so;
   so.num_eliminate_blocks = num_elim;
@@ -208,6 +223,9 @@ void orc_linear_solve(void* h, int num_elim, int solver, int preconditioner, int
   so.max_num_iterations = max_iter;
   so.residual_reset_period = residual_reset_period;
   so.num_threads = nt;
+  so.max_num_spse_iterations = max_num_spse_iterations;
+  so.use_spse_initialization = use_spse_initialization != 0;
+  so.spse_tolerance = spse_tolerance;
   std::unique_ptr<LinearSolverBase> ls;
   const bool s239 = !force_dynamic && Is239(A.bs, num_elim);
   if (solver == ITERATIVE_SCHUR) {
@@ -308,7 +326,7 @@ void* orc_ba_jacobian(void* h) { return &static_cast<BaProgram*>(h)->jacobian; }
 
 struct orc_solve_options {
   int linear_solver, preconditioner, max_num_iterations, max_linear_solver_iterations,
-      min_linear_solver_iterations, jacobi_scaling, num_threads, reserved;
+      min_linear_solver_iterations, jacobi_scaling, num_threads, use_spse_initialization;
   double eta, initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius,
       min_relative_decrease, min_lm_diagonal, max_lm_diagonal, function_tolerance, gradient_tolerance,
       parameter_tolerance;
@@ -322,7 +340,7 @@ void orc_solve_options_default(orc_solve_options* o) {
   o->min_linear_solver_iterations = d.min_linear_solver_iterations;
   o->jacobi_scaling = d.jacobi_scaling;
   o->num_threads = d.num_threads;
-  o->reserved = 0;
+  o->use_spse_initialization = 0;
   o->eta = d.eta;
   o->initial_trust_region_radius = d.initial_trust_region_radius;
   o->max_trust_region_radius = d.max_trust_region_radius;
@@ -350,6 +368,7 @@ int orc_ba_solve(void* h, const orc_solve_options* o, double* state_inout, doubl
   so.min_linear_solver_iterations = o->min_linear_solver_iterations;
   so.jacobi_scaling = o->jacobi_scaling;
   so.num_threads = o->num_threads;
+  so.use_spse_initialization = o->use_spse_initialization;
   so.eta = o->eta;
   so.initial_trust_region_radius = o->initial_trust_region_radius;
   so.max_trust_region_radius = o->max_trust_region_radius;

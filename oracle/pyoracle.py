@@ -163,12 +163,14 @@ class BlockSparseMatrix:
         return y
 
     def linear_solve(self, num_elim, b, D, solver=0, preconditioner=2, min_iter=0, max_iter=500, reset_period=10,
-                     q_tolerance=0.0, r_tolerance=0.0, nt=1, force_dynamic=0):
+                     q_tolerance=0.0, r_tolerance=0.0, nt=1, force_dynamic=0, max_num_spse_iterations=5,
+                     use_spse_initialization=False, spse_tolerance=0.1):
         x = np.zeros(self.num_cols)
         summ = np.zeros(2, dtype=np.int32)
-        lib().orc_linear_solve(self.h, num_elim, solver, preconditioner, min_iter, max_iter, reset_period,
-                               C.c_double(q_tolerance), C.c_double(r_tolerance), _d(_f64(b)), _d(_f64(D)), _d(x),
-                               _i(summ), nt, force_dynamic)
+        lib().orc_linear_solve_spse(self.h, num_elim, solver, preconditioner, min_iter, max_iter, reset_period,
+                                    C.c_double(q_tolerance), C.c_double(r_tolerance), _d(_f64(b)), _d(_f64(D)), _d(x),
+                                    _i(summ), nt, force_dynamic, int(max_num_spse_iterations),
+                                    int(bool(use_spse_initialization)), C.c_double(spse_tolerance))
         return x, int(summ[0]), int(summ[1])
 
 
@@ -202,6 +204,12 @@ class ImplicitSchur:
     def back_substitute(self, x):
         y = np.zeros(self.A.num_cols)
         lib().orc_isc_back_substitute(self.h, _d(_f64(x)), _d(y))
+        return y
+
+    def power_series(self, x, max_num_spse_iterations=5, spse_tolerance=0.0):
+        """PowerSeriesExpansionPreconditioner::RightMultiplyAndAccumulate on a zeroed y (needs want_ftf=True)."""
+        y = np.zeros(self.n)
+        lib().orc_isc_power_series(self.h, int(max_num_spse_iterations), C.c_double(spse_tolerance), _d(_f64(x)), _d(y))
         return y
 
     def ete_inverse(self):
@@ -254,7 +262,7 @@ class BalProblem:
 class SolveOptions(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("linear_solver", "preconditioner", "max_num_iterations",
                                        "max_linear_solver_iterations", "min_linear_solver_iterations",
-                                       "jacobi_scaling", "num_threads", "reserved")] + \
+                                       "jacobi_scaling", "num_threads", "use_spse_initialization")] + \
                [(n, C.c_double) for n in ("eta", "initial_trust_region_radius", "max_trust_region_radius",
                                           "min_trust_region_radius", "min_relative_decrease", "min_lm_diagonal",
                                           "max_lm_diagonal", "function_tolerance", "gradient_tolerance",

@@ -22,7 +22,7 @@
 namespace orc {
 
 enum Termination { SUCCESS = 0, NO_CONVERGENCE = 1, FAILURE = 2, FATAL_ERROR = 3 };
-enum PreconditionerType { IDENTITY = 0, JACOBI = 1, SCHUR_JACOBI = 2 };
+enum PreconditionerType { IDENTITY = 0, JACOBI = 1, SCHUR_JACOBI = 2, SCHUR_POWER_SERIES_EXPANSION = 3 };  // include/ceres/types.h:93-119
 
 // ----------------------------------------------------------------------------
 // PartitionedMatrixView<kR,kE,kF>
@@ -307,6 +307,21 @@ struct ImplicitSchur {
     pmv.LeftMultiplyAndAccumulateF(tmp_rows.data(), y);                          // y = y5 + F' y1
   }
 
+  // :146-174   y += (F'F + D_f^2)^-1 F'E (E'E + D_e^2)^-1 E'F x     (needs compute_ftf_inverse)
+  void InversePowerSeriesOperatorRightMultiplyAccumulate(const double* x, double* y) {
+    std::fill(tmp_rows.begin(), tmp_rows.end(), 0.0);
+    pmv.RightMultiplyAndAccumulateF(x, tmp_rows.data());                         // y1 = F x
+    std::fill(tmp_e_cols.begin(), tmp_e_cols.end(), 0.0);
+    pmv.LeftMultiplyAndAccumulateE(tmp_rows.data(), tmp_e_cols.data());         // y2 = E' y1
+    std::fill(tmp_e_cols_2.begin(), tmp_e_cols_2.end(), 0.0);
+    ete_inv.RightMultiplyAndAccumulate(tmp_e_cols.data(), tmp_e_cols_2.data(), num_threads);  // y3 = (E'E)^-1 y2
+    std::fill(tmp_rows.begin(), tmp_rows.end(), 0.0);
+    pmv.RightMultiplyAndAccumulateE(tmp_e_cols_2.data(), tmp_rows.data());      // y1 = E y3
+    std::fill(tmp_f_cols.begin(), tmp_f_cols.end(), 0.0);
+    pmv.LeftMultiplyAndAccumulateF(tmp_rows.data(), tmp_f_cols.data());         // y4 = F' y1
+    ftf_inv.RightMultiplyAndAccumulate(tmp_f_cols.data(), y, num_threads);       // y += (F'F)^-1 y4
+  }
+
   // :208-243   y = [ (E'E)^-1 E'(b - F x) ; x ]
   void BackSubstitute(const double* x, double* y) {
     const int nr = pmv.A.num_rows;
@@ -335,6 +350,33 @@ struct ImplicitSchur {
     pmv.LeftMultiplyAndAccumulateF(tmp_rows.data(), rhs.data());
   }
 };
+
+// PowerSeriesExpansionPreconditioner::RightMultiplyAndAccumulate (power_series_expansion_preconditioner.cc:57-82):
+// y = sum_{i=0..k} ((F'F)^-1 F'E (E'E)^-1 E'F)^i (F'F)^-1 x, k < max_num_spse_iterations, stopping early once a
+// term's norm drops below spse_tolerance * |first term|.  y is overwritten.
+template <int kR, int kE, int kF>
+void PowerSeriesExpansion(ImplicitSchur<kR, kE, kF>* isc, int max_num_spse_iterations, double spse_tolerance,
+                          const double* x, double* y) {
+  const int n = isc->num_rows();
+  std::vector<double> series_term(n), previous_series_term(n);
+  for (int i = 0; i < n; ++i) y[i] = 0.0;
+  isc->ftf_inv.RightMultiplyAndAccumulate(x, y, isc->num_threads);
+  for (int i = 0; i < n; ++i) previous_series_term[i] = y[i];
+  double sq = 0.0;
+  for (int i = 0; i < n; ++i) sq += y[i] * y[i];
+  const double norm_threshold = spse_tolerance * std::sqrt(sq);
+  for (int i = 1;; ++i) {
+    std::fill(series_term.begin(), series_term.end(), 0.0);
+    isc->InversePowerSeriesOperatorRightMultiplyAccumulate(previous_series_term.data(), series_term.data());
+    double tsq = 0.0;
+    for (int k = 0; k < n; ++k) {
+      y[k] += series_term[k];
+      tsq += series_term[k] * series_term[k];
+    }
+    if (i >= max_num_spse_iterations || std::sqrt(tsq) < norm_threshold) break;
+    std::swap(previous_series_term, series_term);
+  }
+}
 
 // ----------------------------------------------------------------------------
 // BlockRandomAccess{Dense,Diagonal}Matrix: the lhs the eliminator writes into.
@@ -826,6 +868,9 @@ struct IterativeSchurOptions {
   int max_num_iterations = 500;
   int residual_reset_period = 10;
   int num_threads = 1;
+  int max_num_spse_iterations = 5;       // linear_solver.h:172
+  bool use_spse_initialization = false;  // :177
+  double spse_tolerance = 0.1;           // :183
 };
 
 template <int kR, int kE, int kF>
@@ -842,9 +887,12 @@ struct IterativeSchurSolver : LinearSolverBase {
                       double r_tolerance, double* x) override {
     const int num_eliminate_blocks = options.num_eliminate_blocks;
     if (schur_complement == nullptr) {
-      schur_complement.reset(new ImplicitSchur<kR, kE, kF>(*A, num_eliminate_blocks,
-                                                           options.preconditioner_type == JACOBI,
-                                                           options.num_threads));
+      // compute_ftf_inverse: implicit_schur_complement.cc:61-64
+      schur_complement.reset(new ImplicitSchur<kR, kE, kF>(
+          *A, num_eliminate_blocks,
+          options.use_spse_initialization || options.preconditioner_type == JACOBI ||
+              options.preconditioner_type == SCHUR_POWER_SERIES_EXPANSION,
+          options.num_threads));
     }
     schur_complement->Init(D, b);
     const int num_schur_complement_blocks = static_cast<int>(A->bs.cols.size()) - num_eliminate_blocks;
@@ -856,6 +904,9 @@ struct IterativeSchurSolver : LinearSolverBase {
       return summary;
     }
     reduced_solution.assign(schur_complement->num_rows(), 0.0);
+    if (options.use_spse_initialization)  // iterative_schur_complement_solver.cc:100-111
+      PowerSeriesExpansion(schur_complement.get(), options.max_num_spse_iterations, options.spse_tolerance,
+                           schur_complement->rhs.data(), reduced_solution.data());
 
     // CreatePreconditioner (:159-199) + Update (:113-122)
     if (options.preconditioner_type == SCHUR_JACOBI) {
@@ -890,6 +941,9 @@ struct IterativeSchurSolver : LinearSolverBase {
           break;
         case JACOBI:
           schur_complement->ftf_inv.RightMultiplyAndAccumulate(rr, zz, options.num_threads);
+          break;
+        case SCHUR_POWER_SERIES_EXPANSION:  // :178-186: tolerance 0 keeps the preconditioner fixed during CG
+          PowerSeriesExpansion(schur_complement.get(), options.max_num_spse_iterations, 0.0, rr, zz);
           break;
         default: {
           // apply m^-1 blockwise (block_random_access_diagonal_matrix.cc:102-116)

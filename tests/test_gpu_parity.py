@@ -207,6 +207,40 @@ def test_schur_solve_matches_oracle(precond, c16_case, cs):
         assert relerr(x_o, x_exact) < 10 * tol
 
 
+@pytest.mark.parametrize("which", ["c16", "tiny"])
+@pytest.mark.parametrize("mode", ["preconditioner", "initialization", "both"])
+def test_schur_power_series_expansion(which, mode, c16_case, tiny_case, cs):
+    """SCHUR_POWER_SERIES_EXPANSION as preconditioner (iterative_schur_complement_solver.cc:178-186) and
+    use_spse_initialization (:100-111): same iteration counts and solution as the oracle's restatement."""
+    case = c16_case if which == "c16" else tiny_case
+    J, b, D = _scaled_system(case)
+    precond = 3 if mode in ("preconditioner", "both") else 2
+    init = mode in ("initialization", "both")
+    for q_tol, r_tol in ((1e-2, -1.0), (0.0, 1e-8)):
+        x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, preconditioner=precond, q_tolerance=q_tol,
+                                            r_tolerance=r_tol, max_iter=200, nt=8, use_spse_initialization=init)
+        o = case.gpu.solver_options(preconditioner_type=precond, q_tolerance=q_tol, r_tolerance=r_tol,
+                                    max_num_iterations=200, use_spse_initialization=int(init))
+        x, its, term = case.gpu.schur_solve(b, D, o)
+        assert term == term_o
+        assert abs(its - its_o) <= (0 if r_tol < 0 else max(2, its_o // 10))
+        assert relerr(x, x_o) < (1e-8 if r_tol < 0 else 1e-5)
+
+
+def test_lm_trajectory_power_series(tiny_case, cs):
+    """A full LM run with the power-series preconditioner + initial guess against the oracle's (1e-6 per iteration)."""
+    case = tiny_case
+    o = case.orc.default_options()
+    o.preconditioner = 3
+    o.use_spse_initialization = 1
+    _, recs_o, _ = case.orc.solve(case.state, o)
+    lo = case.gpu.lm_options()
+    lo.linear_solver.preconditioner_type = 3
+    lo.linear_solver.use_spse_initialization = 1
+    _, recs = case.gpu.lm_solve(case.state, lo)
+    _compare_traces(recs[:4], recs_o[:4])
+
+
 def test_resident_residuals_and_fused_model_cost(c16_case, cs):
     """b == NULL in b200_schur_solve and b200_model_cost_change use the residuals of the last evaluate (still in HBM):
     same answers as the explicit host-vector forms (trust_region_minimizer.cc:399-402, :430-438)."""

@@ -208,6 +208,82 @@ def test_iterative_schur_vs_dense_qr(oracle, pid, precond, use_D):
     assert np.allclose(x, expect, rtol=0, atol=1e-10)
 
 
+def _spse_setup(oracle, pid=5):
+    """power_series_expansion_preconditioner_test.cc:44-78: fixture 5 with its D, dense S^-1 as the reference."""
+    fx = FIXTURES[pid]
+    A = dense(fx)
+    ne = num_cols_e(fx)
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float)
+    S, rhs, H, g = dense_schur(A, b, D, ne)
+    M = make(oracle, fx)
+    isc = oracle.ImplicitSchur(M, fx["num_eliminate_blocks"], want_ftf=True)
+    isc.init(D, b)
+    return fx, A, ne, D, S, isc, M, b
+
+
+@pytest.mark.parametrize("tolerance", [1e-14, 0.0])
+def test_power_series_expansion_is_the_schur_inverse(oracle, tolerance):
+    """power_series_expansion_preconditioner_test.cc:80-124: 50 terms (tolerance 1e-14 reached, or tolerance 0 and all
+    50 terms) reproduce every column of S^-1 to 1e-14."""
+    fx, A, ne, D, S, isc, M, b = _spse_setup(oracle)
+    Sinv = np.linalg.inv(S)
+    nf = S.shape[0]
+    for i in range(nf):
+        e = np.zeros(nf)
+        e[i] = 1.0
+        y = isc.power_series(e, max_num_spse_iterations=50, spse_tolerance=tolerance)
+        assert np.linalg.norm(y - Sinv[:, i]) < 1e-14
+
+
+def test_power_series_expansion_bad_tolerance_stops_early(oracle):
+    """:126-147: with tolerance 1/eps the series stops after one term and is NOT the inverse."""
+    fx, A, ne, D, S, isc, M, b = _spse_setup(oracle)
+    Sinv = np.linalg.inv(S)
+    nf = S.shape[0]
+    for i in range(nf):
+        e = np.zeros(nf)
+        e[i] = 1.0
+        y = isc.power_series(e, max_num_spse_iterations=50, spse_tolerance=1e14)
+        assert np.linalg.norm(y - Sinv[:, i]) > 1e-14
+
+
+@pytest.mark.parametrize("terms", [1, 2, 5])
+def test_power_series_expansion_partial_sums(oracle, terms):
+    """The k-term value against the dense definition: sum_{i<=k} (M^-1 F'E P E'F)^i M^-1 x, M = F'F + D_f^2."""
+    fx, A, ne, D, S, isc, M_, b = _spse_setup(oracle)
+    E, F = A[:, :ne], A[:, ne:]
+    P = np.linalg.inv(E.T @ E + np.diag(D[:ne] ** 2))
+    Mi = np.linalg.inv(F.T @ F + np.diag(D[ne:] ** 2))
+    T = Mi @ F.T @ E @ P @ E.T @ F
+    rng = np.random.RandomState(7)
+    x = rng.randn(S.shape[0])
+    expect = Mi @ x
+    term = expect.copy()
+    for _ in range(terms):
+        term = T @ term
+        expect = expect + term
+    got = isc.power_series(x, max_num_spse_iterations=terms, spse_tolerance=0.0)
+    assert np.allclose(got, expect, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("pid", [2, 3, 5])
+@pytest.mark.parametrize("spse_init", [False, True])
+def test_iterative_schur_power_series_vs_dense_qr(oracle, pid, spse_init):
+    """SCHUR_POWER_SERIES_EXPANSION as the preconditioner (iterative_schur_complement_solver.cc:178-186) and as the
+    initial guess (:100-111) both reach the DENSE_QR solution."""
+    fx = FIXTURES[pid]
+    A = dense(fx)
+    b = np.array(fx["b"], dtype=float)
+    D = np.array(fx["D"], dtype=float)
+    expect = np.linalg.lstsq(np.vstack([A, np.diag(D)]), np.concatenate([b, np.zeros(A.shape[1])]), rcond=None)[0]
+    M = make(oracle, fx)
+    x, its, term = M.linear_solve(fx["num_eliminate_blocks"], b, D, solver=0, preconditioner=3 if not spse_init else 2,
+                                  r_tolerance=1e-12, max_iter=100, use_spse_initialization=spse_init)
+    assert term == 0
+    assert np.allclose(x, expect, rtol=0, atol=1e-10)
+
+
 @pytest.mark.parametrize("pid", [2, 4, 5, 6])
 def test_dense_schur_vs_dense_qr(oracle, pid):
     """schur_complement_solver_test.cc:127-131: |x - x_qr| / n < 1e-10 with the regulariser on."""
