@@ -34,6 +34,7 @@
 #include "pcg_kernel.cuh"
 #include "pcg_split.cuh"
 #include "spse_kernels.cuh"
+#include "huge_kernels.cuh"
 
 using namespace b200;
 
@@ -198,6 +199,8 @@ struct b200_handle {
   V2View v2{};
   ProblemView view_big{};   // CTA tiles holding only the points with more than 32 rows
   int num_big_tiles = 0;
+  int num_huge = 0;           // points with more than kTile rows (huge_kernels.cuh); their rows appear as chunk tiles
+  int* d_huge_pts = nullptr;
   bool big_folded = false;   // S*x handles them inside schur_mul_v3_kernel (no extra launch)
   int2* d_cta_big = nullptr;
   uint32_t* d_tile_meta = nullptr;
@@ -340,6 +343,13 @@ int tile_grid(b200_handle* h, K kernel, size_t smem) {
   return std::max(1, std::min(h->num_tiles, h->sm_count * per_sm));
 }
 
+// Point-sized entries of the huge points: zeroed before a kernel that accumulates them slice by slice.
+int huge_zero(b200_handle* h, double* d_point_vec) {
+  if (h->num_huge == 0) return B200_OK;
+  return launch(h, K_MISC, [&] { huge_zero3_kernel<<<(3 * h->num_huge + 255) / 256, 256, 0, h->stream>>>(h->num_huge, h->d_huge_pts, d_point_vec); });
+}
+int huge_grid(const b200_handle* h) { return std::max(1, std::min(h->num_huge, h->sm_count * 4)); }
+
 // ------------------------------------------------------------------------------------------------ device-pointer cores
 int sqnorm_dev(b200_handle* h, double* d_out);
 
@@ -361,6 +371,7 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
   const bool with_j = want_jacobian || d_gradient != nullptr;
   const size_t coff = 3 * static_cast<size_t>(h->P);
   if (d_gradient != nullptr) CU(cudaMemsetAsync(d_gradient + coff, 0, sizeof(double) * 9 * h->C, h->stream));
+  if (d_gradient != nullptr) OK(huge_zero(h, d_gradient));
   const size_t smem = tile_smem_bytes<3, 1>();
   int num_partials = h->num_tiles;
   if (with_j && h->v2b_ok) {
@@ -375,6 +386,7 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
     e.loss_type = h->loss_type;
     e.loss_a = h->loss_a;
     if (d_sqnorm != nullptr) CU(cudaMemsetAsync(d_sqnorm + coff, 0, sizeof(double) * 9 * h->C, h->stream));
+    if (d_sqnorm != nullptr) OK(huge_zero(h, d_sqnorm));
     OK(launch(h, K_EVAL_JAC, [&] {
       evaluate_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->eval_v2_smem, h->stream>>>(h->v2_eval, e);
     }));
@@ -421,6 +433,7 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
 
 int sqnorm_dev(b200_handle* h, double* d_out) {
   CU(cudaMemsetAsync(d_out + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
+  OK(huge_zero(h, d_out));
   OK(launch(h, K_SQNORM, [&] {
     sqnorm_kernel<<<h->grid_tile[K_SQNORM], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, d_out);
   }));
@@ -455,6 +468,10 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
       schur_init_kernel<<<h->grid_tile[K_SCHUR_INIT], kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view, st);
     }));
   }
+  if (h->num_huge > 0)
+    OK(launch(h, K_SCHUR_INIT, [&] {
+      huge_schur_init_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, st);
+    }));
   OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
   h->cur_b = d_b;
   h->cur_D = d_D;
@@ -497,6 +514,10 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
       schur_mul_kernel<<<h->grid_tile[K_SCHUR_MUL], kTile, tile_smem_bytes<3, 3>(), h->stream>>>(h->view, h->d_ete_inv, d_x, d_y, done_flag);
     }));
   }
+  if (h->num_huge > 0)
+    OK(launch(h, K_SCHUR_MUL_BIG, [&] {
+      huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_x, d_y, done_flag);
+    }));
   return allreduce_sum(h, d_y, n);
 }
 
@@ -582,6 +603,10 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       OK(launch(h, K_BACKSUB, [&] {
         backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, d_b, h->d_sol, d_x);
       }));
+      if (h->num_huge > 0)
+        OK(launch(h, K_BACKSUB, [&] {
+          huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_b, h->d_sol, d_x);
+        }));
       CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
     }
     return B200_OK;
@@ -604,7 +629,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     });
   };
   // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
-  const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && (h->num_big_tiles == 0 || h->big_folded) &&
+  const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
                        getenv("B200_NO_FUSED_PQ") == nullptr;
   double* pq_parts = fuse_pq ? h->d_pq_parts : nullptr;
   va.pq_parts = pq_parts;
@@ -637,6 +662,10 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
               h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
         }));
       }
+      if (h->num_huge > 0)
+        OK(launch(h, K_SCHUR_MUL_BIG, [&] {
+          huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, vin, out, &h->d_cg->done);
+        }));
       return allreduce_sum(h, out, n);
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
@@ -1136,8 +1165,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     pt_ptr[pt + 1]++;
   }
   for (int k = 0; k < P; ++k) pt_ptr[k + 1] += pt_ptr[k];
-  // Tiles: whole points, <= kTile rows and <= kTile points each.
-  std::vector<TileDesc> tiles;
+  // Tiles: whole points, <= kTile rows and <= kTile points each; a point with more rows becomes chunk tiles.
+  std::vector<TileDesc> tiles, chunk_tiles;
+  std::vector<int> huge_pts;
   {
     int k = 0;
     while (k < P) {
@@ -1145,17 +1175,32 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       t.pt_begin = k;
       t.obs_begin = pt_ptr[k];
       int rows = 0, pts = 0;
+      bool huge = false;
       while (k < P && pts < kTile - 1) {  // pt_count + 1 chunk boundaries are loaded by one thread each
         const int deg = pt_ptr[k + 1] - pt_ptr[k];
         if (deg > kTile) {
-          if (pts == 0)
-            return fail(B200_ERR_UNSUPPORTED, "point %d has %d observations; more than %d per point is not supported yet", k, deg, kTile);
+          huge = pts == 0;
           break;
         }
         if (rows + deg > kTile) break;
         rows += deg;
         ++pts;
         ++k;
+      }
+      if (huge) {  // more than kTile rows: <= kTile-row slices of the one point (TileDesc::chunk)
+        huge_pts.push_back(k);
+        for (int r = pt_ptr[k]; r < pt_ptr[k + 1]; r += kTile) {
+          TileDesc c;
+          c.pt_begin = k;
+          c.pt_count = 1;
+          c.obs_begin = r;
+          c.obs_count = std::min(kTile, pt_ptr[k + 1] - r);
+          c.chunk = 1;
+          tiles.push_back(c);
+          chunk_tiles.push_back(c);
+        }
+        ++k;
+        continue;
       }
       t.obs_count = rows;
       t.pt_count = pts;
@@ -1196,6 +1241,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     int k = 0;
     while (k < P) {
       const int deg0 = pt_ptr[k + 1] - pt_ptr[k];
+      if (deg0 > kTile) {  // huge point: chunk tiles (appended to the big tiles below) + huge_kernels.cuh
+        ++k;
+        continue;
+      }
       if (deg0 > 32) {
         TileDesc t;
         t.pt_begin = k;
@@ -1365,7 +1414,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   OK(dev_alloc(&h->d_state, h->np));
   OK(dev_alloc(&h->d_residuals, 2 * n));
   OK(dev_alloc(&h->d_gradient, h->np));
-  OK(dev_alloc(&h->d_tile_partial, tiles.size() + num_ctas_v2 + big_tiles.size() + 8));
+  OK(dev_alloc(&h->d_tile_partial, tiles.size() + num_ctas_v2 + big_tiles.size() + chunk_tiles.size() + 8));
   OK(dev_alloc(&h->d_fail, 4));
   OK(dev_alloc(&h->d_scalars, 64));
   OK(dev_alloc(&h->d_partial, kRedBlocks * 4));
@@ -1430,7 +1479,18 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaStreamSynchronize(h->stream));
     h->cam_major_ok = true;
   }
+  h->num_huge = static_cast<int>(huge_pts.size());
+  if (h->num_huge > 0) {
+    if (has_dups)
+      return fail(B200_ERR_UNSUPPORTED,
+                  "a point with more than %d observations together with duplicate (camera, point) observations is not supported", kTile);
+    OK(dev_alloc(&h->d_huge_pts, huge_pts.size()));
+    CU(cudaMemcpyAsync(h->d_huge_pts, huge_pts.data(), huge_pts.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
   if (v2_possible) {
+    // the slices of the huge points ride along with the >32-row points in every kernel that has no coupling between the
+    // rows of a point (the partition above only covers the plain ones: cta_big indexes the first part of the array)
+    big_tiles.insert(big_tiles.end(), chunk_tiles.begin(), chunk_tiles.end());
     h->num_big_tiles = static_cast<int>(big_tiles.size());
     TileDesc* d_big = nullptr;
     OK(dev_alloc(&d_big, big_tiles.size()));
@@ -1544,7 +1604,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     // Opt-in experiment (B200_SPLIT_PCG=1): split-phase PCG without any grid-wide barrier (pcg_split.cuh).  Measured
     // within +-1.5 % of the default on the large problems and 13 % slower on C16 (the tests move into the product's
     // prologue): the iteration is bound by its two kernel boundaries, not by the grid sync of the vector kernel.
-    if (h->mul_v4 && h->world == 1 && h->big_folded && h->v2.direct && getenv("B200_SPLIT_PCG") != nullptr) {
+    if (h->mul_v4 && h->world == 1 && h->big_folded && h->v2.direct && h->num_huge == 0 && getenv("B200_SPLIT_PCG") != nullptr) {
       // camera ownership for the D_f^2 p^2 term of p.q: the first CTA whose range contains the camera; every camera
       // must be covered by the (sorted) ranges
       std::vector<int2> own(num_ctas_v2, make_int2(0, 0));
@@ -1580,7 +1640,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     // product launch + one vector launch per iteration (59 vs 43 us per iteration on Ladybug-1723: software grid
     // barriers and the serial vector phases on 148 fat CTAs cost more than two kernel boundaries; see
     // profiles/r01_pcg_persistent_trace_l1723.txt), so the multi-kernel PCG stays the default.
-    if (h->mul_v4 && h->world == 1 && h->big_folded && getenv("B200_PCG_PERSISTENT") != nullptr) {
+    if (h->mul_v4 && h->world == 1 && h->big_folded && h->num_huge == 0 && getenv("B200_PCG_PERSISTENT") != nullptr) {
       const int cpc = (C + num_ctas_v2 - 1) / num_ctas_v2;
       int per_sm = 0;
       if (h->mul_v4_owned) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<true>, 32 * h->v2_mul.warps, h->mul_smem));
@@ -1640,8 +1700,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
 
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
-            "[b200ba] C=%d P=%d N=%d wtiles=%zu big=%zu span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d split=%d\n",
-            C, P, N, wtiles.size(), big_tiles.size(), max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d split=%d\n",
+            C, P, N, wtiles.size(), big_tiles.size(), h->num_huge, max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
             h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
             h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->pcg_ok ? 1 : 0, h->split_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
@@ -1709,7 +1769,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
@@ -1830,6 +1890,7 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
   const size_t off = 3 * static_cast<size_t>(h->P);
   const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
   const int nc = 9 * h->C;
+  OK(huge_zero(h, h->d_vp1));  // point entries of huge points are accumulated slice by slice
   if (h->v2_ok) {
     if (h->v2.direct)
       OK(launch(h, K_MISC, [&] {
@@ -1932,6 +1993,10 @@ int b200_schur_back_substitute(b200_handle* h, const double* z, double* y) {
   OK(launch(h, K_BACKSUB, [&] {
     backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->cur_b, h->d_xr, h->d_y);
   }));
+  if (h->num_huge > 0)
+    OK(launch(h, K_BACKSUB, [&] {
+      huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, h->cur_b, h->d_xr, h->d_y);
+    }));
   OK(d2h(h, y, h->d_y, sizeof(double) * 3 * static_cast<size_t>(h->P)));
   std::memcpy(y + 3 * static_cast<size_t>(h->P), z, sizeof(double) * 9 * h->C);
   return B200_OK;

@@ -18,10 +18,13 @@ namespace b200 {
 constexpr int kTile = 128;  // rows (observations) per tile == threads per CTA
 
 struct TileDesc {
-  int obs_begin;   // first row of the tile
-  int obs_count;   // rows in the tile (> kTile marks a single over-long point, handled by the slow path)
-  int pt_begin;    // first point
-  int pt_count;    // points in the tile
+  int obs_begin = 0;   // first row of the tile
+  int obs_count = 0;   // rows in the tile (<= kTile)
+  int pt_begin = 0;    // first point
+  int pt_count = 0;    // points in the tile
+  int chunk = 0;       // 1: the rows are a slice of the single point pt_begin, which has more than kTile rows: point-sized
+                       // outputs are accumulated with REDs (the caller zeroes them), and the kernels that couple all rows
+                       // of a point skip the tile (huge_kernels.cuh does those points)
 };
 
 struct ProblemView {
@@ -152,7 +155,8 @@ __device__ __forceinline__ void tile_begin(const ProblemView& p, const TileDesc&
       if (load_f) bulk_g2s(s.sF, p.F() + 18 * static_cast<size_t>(d.obs_begin), d.obs_count * 144u, s.bar);
     }
   }
-  if (tid <= d.pt_count) s.sPtOfs[tid] = p.pt_ptr[d.pt_begin + tid] - d.obs_begin;
+  // (clamped to the tile: a chunk tile sees its own rows as the rows of its point)
+  if (tid <= d.pt_count) s.sPtOfs[tid] = min(max(p.pt_ptr[d.pt_begin + tid] - d.obs_begin, 0), d.obs_count);
   if (tid < d.obs_count) s.sCam[tid] = p.cam_idx[d.obs_begin + tid];
   __syncthreads();
   if (tid < d.pt_count) {

@@ -275,9 +275,15 @@ __global__ void __launch_bounds__(kTile) evaluate_kernel(ProblemView p, EvalArgs
           g2 += s.sObs[j * 3 + 2];
         }
         double* gp = a.gradient + 3 * static_cast<size_t>(d.pt_begin + tid);
-        gp[0] = g0;
-        gp[1] = g1;
-        gp[2] = g2;
+        if (d.chunk) {
+          red_add(gp, g0);
+          red_add(gp + 1, g1);
+          red_add(gp + 2, g2);
+        } else {
+          gp[0] = g0;
+          gp[1] = g1;
+          gp[2] = g2;
+        }
       }
     }
     const double total = block_sum<kTile>(cost, s.sPt);
@@ -332,9 +338,15 @@ __global__ void __launch_bounds__(kTile) sqnorm_kernel(ProblemView p, double* ou
         g2 += s.sObs[j * 3 + 2];
       }
       double* op = out + 3 * static_cast<size_t>(d.pt_begin + tid);
-      op[0] = g0;
-      op[1] = g1;
-      op[2] = g2;
+      if (d.chunk) {
+        red_add(op, g0);
+        red_add(op + 1, g1);
+        red_add(op + 2, g2);
+      } else {
+        op[0] = g0;
+        op[1] = g1;
+        op[2] = g2;
+      }
     }
     __syncthreads();
   }
@@ -545,7 +557,18 @@ __global__ void __launch_bounds__(kTile)
         g2 += s.sObs[j * 3 + 2];
       }
       const size_t o = 3 * static_cast<size_t>(d.pt_begin + tid);
-      if (kNormal) {
+      if (d.chunk) {
+        // slice of a huge point: accumulate (kNormal: into the entry the caller zeroed; the D^2 x term once, with the
+        // slice that holds the point's first row)
+        if (kNormal && D != nullptr && p.pt_ptr[d.pt_begin] == d.obs_begin) {
+          g0 += D[o] * D[o] * x[o];
+          g1 += D[o + 1] * D[o + 1] * x[o + 1];
+          g2 += D[o + 2] * D[o + 2] * x[o + 2];
+        }
+        red_add(y + o, g0);
+        red_add(y + o + 1, g1);
+        red_add(y + o + 2, g2);
+      } else if (kNormal) {
         if (D != nullptr) {
           g0 += D[o] * D[o] * x[o];
           g1 += D[o + 1] * D[o + 1] * x[o + 1];
@@ -606,6 +629,7 @@ __global__ void __launch_bounds__(kTile) schur_init_kernel(ProblemView p, SchurS
   uint32_t parity = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const TileDesc d = p.tiles[tile];
+    if (d.chunk) continue;  // slice of a huge point: huge_kernels.cuh
     tile_begin(p, d, s, true, true);
     const bool active = tid < d.obs_count;
     double b0 = 0.0, b1 = 0.0;
@@ -697,6 +721,7 @@ __global__ void __launch_bounds__(kTile)
   uint32_t parity = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const TileDesc d = p.tiles[tile];
+    if (d.chunk) continue;  // slice of a huge point: huge_kernels.cuh
     tile_begin(p, d, s, true, true);
     const bool active = tid < d.obs_count;
     double xc[9];
@@ -783,6 +808,7 @@ __global__ void __launch_bounds__(kTile) backsub_kernel(ProblemView p, const dou
   uint32_t parity = 0;
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const TileDesc d = p.tiles[tile];
+    if (d.chunk) continue;  // slice of a huge point: huge_kernels.cuh
     tile_begin(p, d, s, true, true);
     const bool active = tid < d.obs_count;
     double zc[9], t0 = 0.0, t1 = 0.0;

@@ -345,6 +345,100 @@ def test_ragged_structure_and_duplicates(cs, oracle):
     assert relerr(xg, x_o) < 1e-8
 
 
+def _project(cameras, points, cam_idx, pt_idx):
+    """Snavely projection in numpy (examples/snavely_reprojection_error.h:57-92), only to give the extra rows below
+    plausible observations."""
+    from scipy.spatial.transform import Rotation
+    c = cameras[cam_idx]
+    X = points[pt_idx]
+    Pc = Rotation.from_rotvec(c[:, 0:3]).apply(X) + c[:, 3:6]
+    xp = -Pc[:, 0] / Pc[:, 2]
+    yp = -Pc[:, 1] / Pc[:, 2]
+    r2 = xp * xp + yp * yp
+    d = 1.0 + r2 * (c[:, 7] + c[:, 8] * r2)
+    return np.stack([c[:, 6] * d * xp, c[:, 6] * d * yp], axis=1)
+
+
+@pytest.fixture(scope="module")
+def huge_case(cs, oracle):
+    """Points observed by 129, 150, 257 and all 400 cameras next to ordinary ones: more than kTile = 128 rows per point
+    (chunk tiles + huge_kernels.cuh)."""
+    from ceres_solver_b200 import bal as B
+    rng = np.random.RandomState(11)
+    base = B.synthetic_bal(400, 600, 3000, seed=21, max_degree=40)
+    cam = [base.cam_idx]
+    pt = [base.pt_idx]
+    obs = [base.obs]
+    for point, degree in ((5, 129), (77, 150), (300, 257), (599, 400), (301, 33), (302, 128)):
+        have = set(base.cam_idx[base.pt_idx == point].tolist())
+        extra = [c for c in rng.permutation(400) if c not in have][:max(0, degree - len(have))]
+        extra = np.array(sorted(extra), dtype=base.cam_idx.dtype)
+        pts_i = np.full(extra.size, point, dtype=base.pt_idx.dtype)
+        cam.append(extra)
+        pt.append(pts_i)
+        obs.append(_project(base.cameras, base.points, extra, pts_i) + rng.normal(0.0, 0.5, (extra.size, 2)))
+    bal = B.Bal(np.concatenate(cam), np.concatenate(pt), np.concatenate(obs), base.cameras, base.points)
+    return Case(cs, oracle, bal)
+
+
+def test_huge_points_components(huge_case, oracle):
+    case = huge_case
+    deg = np.bincount(case.rp.row_pt)
+    assert deg.max() == 400 and (deg > 128).sum() == 4
+    (cost, res, grad), (cost_o, res_o, grad_o) = _evaluate_both(case)
+    assert abs(cost - cost_o) <= 1e-12 * abs(cost_o)
+    assert relerr(res, res_o) < 1e-12
+    assert relerr(grad, grad_o) < 1e-11
+    J = case.orc.jacobian()
+    assert relerr(case.gpu.jacobian_values(), J.values()) < 1e-12
+    assert relerr(case.gpu.squared_column_norm(), J.squared_column_norm()) < 1e-12
+    rng = np.random.RandomState(3)
+    x = rng.randn(case.gpu.num_parameters)
+    v = rng.randn(case.gpu.num_residuals)
+    assert relerr(case.gpu.right_multiply(x), J.right_multiply(x, nt=8)) < 1e-12
+    assert relerr(case.gpu.left_multiply(v), J.left_multiply(v, nt=8)) < 1e-12
+    Dn = np.abs(rng.randn(case.gpu.num_parameters)) + 0.1
+    jx = J.right_multiply(x, nt=8)
+    assert relerr(case.gpu.jtj_multiply(x, Dn), J.left_multiply(jx, nt=8) + Dn * Dn * x) < 1e-12
+
+
+def test_huge_points_schur(huge_case, oracle, cs):
+    case = huge_case
+    J, b, D = _scaled_system(case)
+    isc = oracle.ImplicitSchur(J, case.gpu.P, want_ftf=True, nt=8)
+    isc.init(D, b)
+    case.gpu.schur_init(b, D)
+    assert relerr(case.gpu.schur_ete_inverse(), isc.ete_inverse()) < 1e-11
+    assert relerr(case.gpu.schur_rhs(), isc.rhs()) < 1e-10
+    rng = np.random.RandomState(2)
+    for _ in range(2):
+        x = rng.randn(9 * case.gpu.C)
+        assert relerr(case.gpu.schur_multiply(x), isc.right_multiply(x)) < 1e-10
+    z = rng.randn(9 * case.gpu.C)
+    assert relerr(case.gpu.schur_back_substitute(z), isc.back_substitute(z)) < 1e-10
+    C = case.gpu.C
+    diag, _ = J.schur_eliminate(case.gpu.P, None, D, diagonal_only=True, diag_len=81 * C, nt=8, n_f=9 * C)
+    blocks, _ = case.gpu.schur_jacobi_update()
+    assert relerr(blocks, diag) < 1e-10
+    for precond in (1, 2):
+        x_o, its_o, term_o = J.linear_solve(case.gpu.P, b, D, solver=0, preconditioner=precond, q_tolerance=1e-3,
+                                            r_tolerance=-1.0, nt=8)
+        xg, its, term = case.gpu.schur_solve(b, D, case.gpu.solver_options(preconditioner_type=precond, q_tolerance=1e-3,
+                                                                           r_tolerance=-1.0))
+        assert (its, term) == (its_o, term_o)
+        assert relerr(xg, x_o) < 1e-8
+
+
+@pytest.mark.parametrize("host_boundary", [False, True])
+def test_huge_points_lm_trajectory(host_boundary, huge_case):
+    case = huge_case
+    o = case.orc.default_options()
+    o.num_threads = 8
+    state_o, recs_o, _ = case.orc.solve(case.state, o)
+    state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(), host_boundary=host_boundary)
+    _compare_traces(recs[:4], recs_o[:4])
+
+
 def test_argument_errors(cs):
     with pytest.raises(cs.B200Error) as e:
         cs.Problem(2, 3, [0, 1, 0], [0, 2, 1], np.zeros(6))  # rows not grouped by e block
