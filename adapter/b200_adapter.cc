@@ -165,4 +165,28 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
   return summary;
 }
 
+// ---------------------------------------------------------------- B200DenseSchurSolver
+LinearSolver::Summary B200DenseSchurSolver::SolveImpl(BlockSparseMatrix* A, const double* b,
+                                                      const LinearSolver::PerSolveOptions& per_solve_options, double* x) {
+  LinearSolver::Summary summary;
+  auto* jac = dynamic_cast<B200Jacobian*>(A);
+  if (jac == nullptr) {
+    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+    summary.message = "B200DenseSchurSolver needs the Jacobian created by B200Evaluator.";
+    return summary;
+  }
+  b200_solver_summary s{};
+  const double* b_arg = (b == jac->context().last_residuals) ? nullptr : b;
+  if (b200_dense_schur_solve(jac->handle(), b_arg, per_solve_options.D, x, &s) != B200_OK) {
+    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+    summary.message = b200_last_error();
+    return summary;
+  }
+  summary.num_iterations = s.num_iterations;
+  summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);
+  if (summary.termination_type == LinearSolverTerminationType::FAILURE)
+    summary.message = "Cholesky failure: the reduced camera system is not positive definite.";
+  return summary;
+}
+
 }  // namespace ceres::internal

@@ -98,5 +98,17 @@ class B200IterativeSchurSolver final : public BlockSparseMatrixSolver {
   LinearSolver::Options options_;
 };
 
+// DENSE_SCHUR / SPARSE_SCHUR on the device: explicit reduced camera system + Cholesky (b200_dense_schur_solve), the exact
+// solve DenseSchurComplementSolver / SparseSchurComplementSolver perform (schur_complement_solver.cc:101-214, :224-408).
+class B200DenseSchurSolver final : public BlockSparseMatrixSolver {
+ public:
+  explicit B200DenseSchurSolver(LinearSolver::Options options) : options_(std::move(options)) {}
+
+ private:
+  LinearSolver::Summary SolveImpl(BlockSparseMatrix* A, const double* b,
+                                  const LinearSolver::PerSolveOptions& per_solve_options, double* x) final;
+  LinearSolver::Options options_;
+};
+
 }  // namespace ceres::internal
 #endif  // CERES_INTERNAL_B200_ADAPTER_H_

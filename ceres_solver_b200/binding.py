@@ -19,6 +19,7 @@ OK = 0
 ERR_EVALUATION_FAILED = -3
 LS_SUCCESS, LS_NO_CONVERGENCE, LS_FAILURE, LS_FATAL_ERROR = 0, 1, 2, 3
 PRECOND_IDENTITY, PRECOND_JACOBI, PRECOND_SCHUR_JACOBI, PRECOND_SCHUR_POWER_SERIES_EXPANSION = 0, 1, 2, 3
+ITERATIVE_SCHUR, DENSE_SCHUR = 0, 1
 LOSS_TRIVIAL, LOSS_HUBER = 0, 1
 
 
@@ -49,7 +50,7 @@ class SolverSummary(C.Structure):
 
 class LmOptions(C.Structure):
     _fields_ = [("max_num_iterations", C.c_int32), ("jacobi_scaling", C.c_int32),
-                ("max_num_consecutive_invalid_steps", C.c_int32), ("reserved", C.c_int32), ("eta", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int32), ("linear_solver_type", C.c_int32), ("eta", C.c_double),
                 ("initial_trust_region_radius", C.c_double), ("max_trust_region_radius", C.c_double),
                 ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
                 ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double), ("function_tolerance", C.c_double),
@@ -76,7 +77,7 @@ SYMBOLS = [
     "b200_num_residuals", "b200_evaluate", "b200_plus", "b200_jacobian_squared_column_norm",
     "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply", "b200_model_cost_change",
     "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_jtj_multiply", "b200_solver_options_default",
-    "b200_schur_solve", "b200_schur_init", "b200_schur_rhs", "b200_schur_ete_inverse", "b200_schur_multiply",
+    "b200_schur_solve", "b200_dense_schur_solve", "b200_schur_init", "b200_schur_rhs", "b200_schur_ete_inverse", "b200_schur_multiply",
     "b200_schur_back_substitute", "b200_schur_jacobi_update", "b200_block_jacobi_update",
     "b200_lm_options_default", "b200_lm_solve", "b200_profile_enable", "b200_stats_reset", "b200_stats_get",
     "b200_total_launches", "b200_synchronize", "b200_transfer_bytes",
@@ -222,6 +223,13 @@ class Problem:
         s = SolverSummary()
         bp = _d(_f64(b)) if b is not None else None  # None: the residuals of the last evaluate(), still in HBM
         _check(lib().b200_schur_solve(self.h, bp, _d(_f64(D)), C.byref(o), _d(x), C.byref(s)))
+        return x, s.num_iterations, s.termination_type
+
+    def dense_schur_solve(self, b, D):
+        x = np.full(self.num_parameters, np.nan)
+        s = SolverSummary()
+        bp = _d(_f64(b)) if b is not None else None
+        _check(lib().b200_dense_schur_solve(self.h, bp, _d(_f64(D)), _d(x), C.byref(s)))
         return x, s.num_iterations, s.termination_type
 
     def model_cost_change(self, step):

@@ -35,6 +35,7 @@
 #include "pcg_split.cuh"
 #include "spse_kernels.cuh"
 #include "huge_kernels.cuh"
+#include "dense_schur.cuh"
 
 using namespace b200;
 
@@ -90,6 +91,41 @@ const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squa
                                      "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
                                      "schur_multiply", "schur_multiply_big_points", "camera_reduce", "schur_diag_blocks", "invert_9x9", "back_substitute",
                                      "model_cost", "cg_vector", "pcg_persistent", "lm_vector", "misc"};
+
+// cuSOLVER (dense Cholesky of the explicit reduced camera system) is bound lazily with dlopen like NCCL: the
+// library is only touched by b200_dense_schur_solve, and shares whatever libcusolver.so.11 the process already has.
+struct CusolverApi {
+  typedef int (*create_t)(void**);
+  typedef int (*destroy_t)(void*);
+  typedef int (*set_stream_t)(void*, cudaStream_t);
+  typedef int (*potrf_bs_t)(void*, int, int, double*, int, int*);
+  typedef int (*potrf_t)(void*, int, int, double*, int, double*, int, int*);
+  typedef int (*potrs_t)(void*, int, int, int, const double*, int, double*, int, int*);
+  create_t Create = nullptr;
+  destroy_t Destroy = nullptr;
+  set_stream_t SetStream = nullptr;
+  potrf_bs_t DpotrfBufferSize = nullptr;
+  potrf_t Dpotrf = nullptr;
+  potrs_t Dpotrs = nullptr;
+  bool ok = false;
+};
+CusolverApi g_cusolver;
+bool load_cusolver() {
+  if (g_cusolver.ok) return true;
+  const char* name = getenv("B200_CUSOLVER_LIB");
+  void* lib = dlopen(name != nullptr ? name : "libcusolver.so.11", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) lib = dlopen("libcusolver.so", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) return false;
+  g_cusolver.Create = reinterpret_cast<CusolverApi::create_t>(dlsym(lib, "cusolverDnCreate"));
+  g_cusolver.Destroy = reinterpret_cast<CusolverApi::destroy_t>(dlsym(lib, "cusolverDnDestroy"));
+  g_cusolver.SetStream = reinterpret_cast<CusolverApi::set_stream_t>(dlsym(lib, "cusolverDnSetStream"));
+  g_cusolver.DpotrfBufferSize = reinterpret_cast<CusolverApi::potrf_bs_t>(dlsym(lib, "cusolverDnDpotrf_bufferSize"));
+  g_cusolver.Dpotrf = reinterpret_cast<CusolverApi::potrf_t>(dlsym(lib, "cusolverDnDpotrf"));
+  g_cusolver.Dpotrs = reinterpret_cast<CusolverApi::potrs_t>(dlsym(lib, "cusolverDnDpotrs"));
+  g_cusolver.ok = g_cusolver.Create && g_cusolver.Destroy && g_cusolver.SetStream && g_cusolver.DpotrfBufferSize &&
+                  g_cusolver.Dpotrf && g_cusolver.Dpotrs;
+  return g_cusolver.ok;
+}
 
 #ifdef B200_WITH_NCCL
 // NCCL is bound lazily with dlopen/dlsym, and only when world_size > 1: the library then shares whatever
@@ -199,10 +235,16 @@ struct b200_handle {
   V2View v2{};
   ProblemView view_big{};   // CTA tiles holding only the points with more than 32 rows
   int num_big_tiles = 0;
+  double* d_dense_s = nullptr;   // explicit reduced camera system [9C][9C] (allocated by the first dense solve)
+  double* d_dense_work = nullptr;
+  int dense_lwork = 0;
+  int* d_dense_info = nullptr;
+  void* cusolver = nullptr;
   int num_huge = 0;           // points with more than kTile rows (huge_kernels.cuh); their rows appear as chunk tiles
   int* d_huge_pts = nullptr;
   bool big_folded = false;   // S*x handles them inside schur_mul_v3_kernel (no extra launch)
   int2* d_cta_big = nullptr;
+  int2* d_cta_big_none = nullptr;
   uint32_t* d_tile_meta = nullptr;
   bool mul_v4 = false, mul_v4_owned = false;
   bool residuals_resident = false;  // d_residuals holds the residuals of the last b200_evaluate(..., residuals != NULL)
@@ -887,6 +929,60 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   return finish();
 }
 
+// DenseSchurComplementSolver (schur_complement_solver.cc:101-159, :161-214) on device pointers: explicit S by
+// dense_schur_assemble_kernel, Cholesky by cuSOLVER, back substitution by the implicit-Schur kernels.
+int dense_schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, double* d_x, b200_solver_summary* summary) {
+  if (h->world > 1) return fail(B200_ERR_UNSUPPORTED, "the explicit Schur complement is single-GPU");
+  const int n = 9 * h->C;
+  const size_t bytes = sizeof(double) * static_cast<size_t>(n) * n;
+  if (bytes > (static_cast<size_t>(48) << 30))
+    return fail(B200_ERR_UNSUPPORTED, "dense reduced camera system of %d cameras needs %.1f GB", h->C, bytes / 1e9);
+  if (!load_cusolver()) return fail(B200_ERR_UNSUPPORTED, "cannot load libcusolver.so.11: %s", dlerror());
+  if (h->cusolver == nullptr) {
+    if (g_cusolver.Create(&h->cusolver) != 0) return fail(B200_ERR_CUDA, "cusolverDnCreate failed");
+    if (g_cusolver.SetStream(h->cusolver, h->stream) != 0) return fail(B200_ERR_CUDA, "cusolverDnSetStream failed");
+  }
+  if (h->d_dense_s == nullptr) {
+    OK(dev_alloc(&h->d_dense_s, static_cast<size_t>(n) * n));
+    OK(dev_alloc(&h->d_dense_info, 4));
+    int lwork = 0;
+    if (g_cusolver.DpotrfBufferSize(h->cusolver, /*CUBLAS_FILL_MODE_LOWER*/ 0, n, h->d_dense_s, n, &lwork) != 0)
+      return fail(B200_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+    h->dense_lwork = std::max(lwork, 1);
+    OK(dev_alloc(&h->d_dense_work, static_cast<size_t>(h->dense_lwork)));
+  }
+  OK(schur_init_dev(h, d_b, d_D));   // (E'E + D^2)^-1 and the reduced right-hand side
+  const double* Df = d_D != nullptr ? d_D + 3 * static_cast<size_t>(h->P) : nullptr;
+  CU(cudaMemsetAsync(h->d_dense_s, 0, bytes, h->stream));
+  OK(launch(h, K_DIAG_BLOCKS, [&] {
+    dense_schur_assemble_kernel<<<std::max(1, std::min(h->P, h->sm_count * 8)), kDsThreads, 0, h->stream>>>(h->view, h->d_ete_inv, h->d_dense_s, static_cast<size_t>(n));
+  }));
+  OK(launch(h, K_MISC, [&] { dense_schur_diagonal_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, Df, h->d_dense_s, static_cast<size_t>(n)); }));
+  if (g_cusolver.Dpotrf(h->cusolver, 0, n, h->d_dense_s, n, h->d_dense_work, h->dense_lwork, h->d_dense_info) != 0)
+    return fail(B200_ERR_CUDA, "cusolverDnDpotrf failed");
+  CU(cudaMemcpyAsync(h->d_sol, h->d_rhs, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+  if (g_cusolver.Dpotrs(h->cusolver, 0, n, 1, h->d_dense_s, n, h->d_sol, n, h->d_dense_info + 1) != 0)
+    return fail(B200_ERR_CUDA, "cusolverDnDpotrs failed");
+  CU(cudaMemcpyAsync(h->h_fail, h->d_dense_info, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  summary->num_iterations = 1;   // schur_complement_solver.cc:154
+  summary->residual_norm = 0.0;
+  if (h->h_fail[0] != 0 || h->h_fail[1] != 0) {   // not positive definite: LinearSolverTerminationType::FAILURE (:203-210)
+    summary->termination_type = B200_LS_FAILURE;
+    return B200_OK;
+  }
+  summary->termination_type = B200_LS_SUCCESS;
+  OK(launch(h, K_BACKSUB, [&] {
+    backsub_kernel<<<h->grid_tile[K_BACKSUB], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_ete_inv, d_b, h->d_sol, d_x);
+  }));
+  if (h->num_huge > 0)
+    OK(launch(h, K_BACKSUB, [&] {
+      huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_b, h->d_sol, d_x);
+    }));
+  CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+
 int reduce_partials(b200_handle* h, int blocks, int slots, unsigned op_mask, double* host_out, bool across_ranks) {
   OK(launch(h, K_LM_VEC, [&] { reduce_final_kernel<<<1, 32, 0, h->stream>>>(blocks, slots, op_mask, h->d_partial, h->d_scalars + 8); }));
 #ifdef B200_WITH_NCCL
@@ -1118,7 +1214,7 @@ void b200_lm_options_default(b200_lm_options* o) {
   o->max_num_iterations = 5;
   o->jacobi_scaling = 1;
   o->max_num_consecutive_invalid_steps = 5;
-  o->reserved = 0;
+  o->linear_solver_type = B200_ITERATIVE_SCHUR;
   o->eta = 1e-2;
   o->initial_trust_region_radius = 1e4;
   o->max_trust_region_radius = 1e16;
@@ -1600,6 +1696,14 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     // function attributes are process-wide: always raise them to the device limit, never to this handle's need
     CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+    if (!h->big_folded) {
+      // the S*x kernel must not take the >32-row points itself when they are handled by a separate launch
+      int2* none = nullptr;
+      OK(dev_alloc(&none, static_cast<size_t>(num_ctas_v2)));
+      CU(cudaMemsetAsync(none, 0, sizeof(int2) * num_ctas_v2, h->stream));
+      h->d_cta_big_none = none;
+      h->v2_mul.cta_big = none;
+    }
     h->v2_ok = true;
     // Opt-in experiment (B200_SPLIT_PCG=1): split-phase PCG without any grid-wide barrier (pcg_split.cuh).  Measured
     // within +-1.5 % of the default on the large problems and 13 % slower on C16 (the tests move into the product's
@@ -1769,11 +1873,12 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
   if (h->h_scalars) cudaFreeHost(h->h_scalars);
+  if (h->cusolver != nullptr && g_cusolver.ok) g_cusolver.Destroy(h->cusolver);
   if (h->h_cg) cudaFreeHost(h->h_cg);
   for (cudaEvent_t e : h->ev_cg)
     if (e != nullptr) cudaEventDestroy(e);
@@ -1950,6 +2055,22 @@ int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b20
   OK(schur_solve_dev(h, d_b, D != nullptr ? h->d_D : nullptr, opts, h->d_y, summary));
   if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR)
     OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
+  return B200_OK;
+}
+
+int b200_dense_schur_solve(b200_handle* h, const double* b, const double* D, double* x, b200_solver_summary* summary) {
+  if (h == nullptr || x == nullptr || summary == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (b == nullptr && !h->residuals_resident)
+    return fail(B200_ERR_INVALID_ARGUMENT, "b == NULL means the residuals of the last b200_evaluate, and there are none");
+  CU(cudaSetDevice(h->device));
+  const double* d_b = h->d_residuals;
+  if (b != nullptr) {
+    OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    d_b = h->d_b;
+  }
+  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  OK(dense_schur_solve_dev(h, d_b, D != nullptr ? h->d_D : nullptr, h->d_y, summary));
+  if (summary->termination_type == B200_LS_SUCCESS) OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
   return B200_OK;
 }
 
@@ -2145,7 +2266,8 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
         for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
       }
       std::fill(sol.begin(), sol.end(), std::numeric_limits<double>::quiet_NaN());  // levenberg_marquardt_strategy.cc:108
-      OK(b200_schur_solve(h, nullptr /* residuals of the last evaluate, still in HBM */, lmD.data(), &so, sol.data(), &ls));
+      if (opt->linear_solver_type == B200_DENSE_SCHUR) OK(b200_dense_schur_solve(h, nullptr, lmD.data(), sol.data(), &ls));
+      else OK(b200_schur_solve(h, nullptr /* residuals of the last evaluate, still in HBM */, lmD.data(), &so, sol.data(), &ls));
       if (ls.termination_type != B200_LS_FAILURE && ls.termination_type != B200_LS_FATAL_ERROR) {
         // step = -sol, delta = step * scaling, candidate = x + delta (Evaluator::Plus on Euclidean blocks) and the two
         // norms the minimizer needs, in one pass
@@ -2169,7 +2291,8 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
         lm_diagonal_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, reuse_diagonal ? 0 : 1, h->d_sqnorm, h->d_diagonal, h->d_lmD,
                                                                           opt->min_lm_diagonal, opt->max_lm_diagonal, radius);
       }));
-      OK(schur_solve_dev(h, h->d_residuals, h->d_lmD, &so, h->d_y, &ls));
+      if (opt->linear_solver_type == B200_DENSE_SCHUR) OK(dense_schur_solve_dev(h, h->d_residuals, h->d_lmD, h->d_y, &ls));
+      else OK(schur_solve_dev(h, h->d_residuals, h->d_lmD, &so, h->d_y, &ls));
     }
     reuse_diagonal = true;
     it.linear_solver_iterations = ls.num_iterations;

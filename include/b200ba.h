@@ -49,6 +49,9 @@ enum {
   B200_PRECOND_SCHUR_POWER_SERIES_EXPANSION = 3 /* power_series_expansion_preconditioner.cc:57-82 */
 };
 enum { B200_LOSS_TRIVIAL = 0, B200_LOSS_HUBER = 1 };
+/* LinearSolverType subset (include/ceres/types.h): the implicit iterative solver and the exact solve on the explicit
+ * reduced camera system (DENSE_SCHUR; stands in for SPARSE_SCHUR too: both are exact solves of the same system). */
+enum { B200_ITERATIVE_SCHUR = 0, B200_DENSE_SCHUR = 1 };
 
 /* Problem structure = what the adapters read off the reduced ceres::internal::Program
  * (residual_block->parameter_blocks()[j]->index(), SnavelyReprojectionError::observed_x/y,
@@ -129,6 +132,11 @@ void b200_solver_options_default(b200_solver_options* o);
 int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b200_solver_options* opts,
                      double* x, b200_solver_summary* summary);
 
+/* DenseSchurComplementSolver::SolveImpl (schur_complement_solver.cc:101-159, :161-214): explicit reduced camera system
+ * S (dense 9C x 9C, assembled on the device), Cholesky (cuSOLVER potrf/potrs, loaded lazily), back substitution.
+ * Single GPU, 9C up to ~75k.  summary: num_iterations 1, SUCCESS or FAILURE (S not positive definite). b == NULL as above. */
+int b200_dense_schur_solve(b200_handle* h, const double* b, const double* D, double* x, b200_solver_summary* summary);
+
 /* Finer-grained pieces of the same solve, for parity tests (each mirrors one reference class):
  *   ImplicitSchurComplement::Init / rhs / RightMultiplyAndAccumulate / BackSubstitute
  *     (implicit_schur_complement.cc:49-97, :251-276, :106-144, :208-243)
@@ -148,7 +156,7 @@ typedef struct b200_lm_options { /* Solver::Options subset, include/ceres/solver
   int32_t max_num_iterations;              /* bundle_adjuster.cc:121 (5) */
   int32_t jacobi_scaling;                  /* 1 */
   int32_t max_num_consecutive_invalid_steps; /* 5 */
-  int32_t reserved;
+  int32_t linear_solver_type;        /* B200_ITERATIVE_SCHUR (default) or B200_DENSE_SCHUR */
   double eta;                              /* 1e-2 */
   double initial_trust_region_radius;      /* 1e4 */
   double max_trust_region_radius;          /* 1e16 */

@@ -991,6 +991,7 @@ struct DenseSchurSolver : LinearSolverBase {
     summary.termination_type = SUCCESS;
     const int n = lhs->n;
     if (n > 0) {
+      summary.num_iterations = 1;  // schur_complement_solver.cc:199
       // In-place dense Cholesky on the upper triangle (what selfadjointView<Upper>().llt() reads).
       std::vector<double>& S = lhs->values;
       std::vector<double> L(static_cast<size_t>(n) * n, 0.0);

@@ -439,6 +439,41 @@ def test_huge_points_lm_trajectory(host_boundary, huge_case):
     _compare_traces(recs[:4], recs_o[:4])
 
 
+@pytest.mark.parametrize("which", ["c16", "tiny", "huge"])
+def test_dense_schur_solve(which, c16_case, tiny_case, huge_case, cs):
+    """explicit reduced camera system + Cholesky (schur_complement_solver.cc:101-214) against the oracle's
+    DENSE_SCHUR (an exact solve of the same damped normal equations)."""
+    case = {"c16": c16_case, "tiny": tiny_case, "huge": huge_case}[which]
+    J, b, D = _scaled_system(case)
+    x_o, _, term_o = J.linear_solve(case.gpu.P, b, D, solver=1, nt=8)
+    x, its, term = case.gpu.dense_schur_solve(b, D)
+    assert term == term_o == cs.LS_SUCCESS and its == 1
+    assert relerr(x, x_o) < 1e-8
+    # the same answer from the device-resident residuals
+    x2, _, _ = case.gpu.dense_schur_solve(None, D)
+    assert relerr(x2, x) < 1e-12
+    # and the iterative solver converges to it
+    xi, _, ti = case.gpu.schur_solve(b, D, case.gpu.solver_options(q_tolerance=0.0, r_tolerance=1e-12))
+    assert relerr(xi, x) < 1e-5
+
+
+@pytest.mark.parametrize("host_boundary", [False, True])
+def test_lm_trajectory_dense_schur(host_boundary, c16_case, cs):
+    """BASELINE.json configs[0]'s exact-step LM loop (bundle_adjuster defaults with a Schur-based exact solver): the
+    GPU loop with B200_DENSE_SCHUR against the oracle's DENSE_SCHUR loop, which reproduces the reference's published
+    transcript digit for digit (tests/test_oracle_ba.py)."""
+    case = c16_case
+    o = case.orc.default_options()
+    o.linear_solver = 1
+    o.num_threads = 8
+    state_o, recs_o, _ = case.orc.solve(case.state, o)
+    lo = case.gpu.lm_options()
+    lo.linear_solver_type = cs.DENSE_SCHUR
+    state, recs = case.gpu.lm_solve(case.state, lo, host_boundary=host_boundary)
+    _compare_traces(recs, recs_o)
+    assert relerr(state, state_o) < 1e-6
+
+
 def test_argument_errors(cs):
     with pytest.raises(cs.B200Error) as e:
         cs.Problem(2, 3, [0, 1, 0], [0, 2, 1], np.zeros(6))  # rows not grouped by e block
