@@ -677,6 +677,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   va.pq_parts = pq_parts;
   va.num_pq_parts = fuse_pq ? h->v2.num_ctas : 0;
   va.seed_pq = fuse_pq ? h->d_seed_pq : nullptr;
+  const bool use_pdl = getenv("B200_NO_PDL") == nullptr && !h->profiling;
   auto product = [&](const double* vin, double* out) -> int {
     if (seeded) {
       // The handful of >32-row points runs on a side stream, concurrently with the warp-tile kernel (both only add
@@ -691,8 +692,22 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         CU(cudaEventRecord(h->ev_join, h->stream2));
       }
       OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done, pq_parts);
-        else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done, pq_parts);
+        if (h->mul_v4) {
+          // programmatic dependent launch: the product's prologue overlaps the tail of the vector kernel before it
+          cudaLaunchConfig_t cfg{};
+          cfg.gridDim = dim3(h->v2.num_ctas);
+          cfg.blockDim = dim3(32 * h->v2_mul.warps);
+          cfg.dynamicSmemBytes = h->mul_smem;
+          cfg.stream = h->stream;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          const int* done_ptr = &h->d_cg->done;
+          if (h->mul_v4_owned) cudaLaunchKernelEx(&cfg, schur_mul_v4_kernel<true>, h->v2_mul, static_cast<const double*>(h->d_ete_inv), vin, out, done_ptr, pq_parts);
+          else cudaLaunchKernelEx(&cfg, schur_mul_v4_kernel<false>, h->v2_mul, static_cast<const double*>(h->d_ete_inv), vin, out, done_ptr, pq_parts);
+        }
         else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
         else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));

@@ -92,6 +92,9 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   __shared__ double scratch[kCgThreads / 32][3];
   __shared__ double s_tot[4];
   __shared__ double s_r[kCgCamsPerCta * 9];
+  // lets a product kernel launched with programmatic stream serialisation start its prologue now (it waits for this
+  // grid's completion before it touches anything this kernel writes)
+  asm volatile("griddepcontrol.launch_dependents;");
   CgState* st = a.st;
   const int mode = a.mode;
   // state of the previous iteration, read before anybody rewrites it; all the loads that do not depend on a grid-wide

@@ -809,13 +809,20 @@ template <bool kOwned>
 __global__ void __launch_bounds__(kV4MaxThreads, 1)
     schur_mul_v4_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
                         const int* __restrict__ done_flag, double* pq_part) {
-  if (done_flag != nullptr && *done_flag != 0) return;
+  // Everything up to the wait below only touches data that is constant during a PCG (J, (E'E)^-1, the tile tables), so
+  // that with programmatic dependent launch this prologue and the first TMA requests overlap the tail of the vector
+  // kernel that produces x (griddepcontrol.wait is a no-op for an ordinary launch).
   const V4Ctx c = v4_ctx(v);
   v4_init(v, c);
   v4_prime(v, ete_inv, c);
   {
     const int n = c.sy_stride * v.replicas;
     for (int i = threadIdx.x; i < n; i += blockDim.x) c.sy()[i] = 0.0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (done_flag != nullptr && __ldcg(done_flag) != 0) {  // PCG already terminated: nothing to do but let the TMA land
+      v4_drain(v, c, 0);
+      return;
+    }
     const double* xs = x + 9 * static_cast<size_t>(c.cr.x);
     for (int i = threadIdx.x; i < 9 * (c.cr.y - c.cr.x); i += blockDim.x) c.sx()[i] = __ldcg(xs + i);
   }

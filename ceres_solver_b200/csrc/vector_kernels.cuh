@@ -2,9 +2,10 @@
 //
 // The PCG of the reference (conjugate_gradients_solver.h:109-306) runs ~12 tiny Eigen expressions and
 // 3 dot products per iteration, each a host round trip in its CUDA variant (cuda_vector.cc:97-181).  Here one
-// single-CTA kernel before and one after the S*p product carry all of it, with every scalar (rho, alpha,
-// beta, Q, |r|, iteration count, termination code) living in a device-side CgState so that the host never
-// synchronises inside the iteration: kernels exit immediately once `done` is set.
+// cooperative kernel per iteration (cg_kernel.cuh) carries all of it, with every scalar (rho, alpha, beta, Q, |r|,
+// iteration count, termination code) living in a device-side CgState so that the host never synchronises inside the
+// iteration: kernels exit immediately once `done` is set.  This header holds the state, the small helpers and the
+// parameter-sized LM vector kernels.
 #pragma once
 #include "common.cuh"
 
@@ -27,192 +28,6 @@ struct CgParams {
 };
 
 __device__ __forceinline__ bool zero_or_inf(double x) { return x == 0.0 || isinf(x); }
-
-// x = 0 (the reference starts ITERATIVE_SCHUR from zero, iterative_schur_complement_solver.cc:98-99),
-// r = rhs - S*0 = rhs, Q0 = 0, rho = 1   (conjugate_gradients_solver.h:131-160)
-__global__ void __launch_bounds__(kVecThreads)
-    cg_begin_kernel(CgParams prm, const double* __restrict__ rhs, double* x, double* r, CgState* st) {
-  __shared__ double scratch[32];
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < prm.n; i += blockDim.x) {
-    const double v = rhs[i];
-    x[i] = 0.0;
-    r[i] = v;
-    acc += v * v;
-  }
-  const double sq = block_sum<kVecThreads>(acc, scratch);
-  if (threadIdx.x == 0) {
-    const double norm_rhs = sqrt(sq);
-    st->norm_rhs = norm_rhs;
-    st->tol_r = prm.r_tolerance * norm_rhs;
-    st->norm_r = norm_rhs;
-    st->rho = 1.0;
-    st->last_rho = 1.0;
-    st->Q0 = 0.0;
-    st->iteration = 0;
-    st->done = 0;
-    st->termination = 1;  // NO_CONVERGENCE until proven otherwise
-    st->reason = 0;
-    if (norm_rhs == 0.0) {
-      st->done = 1;
-      st->termination = 0;
-      st->reason = 8;
-    } else if (prm.min_iterations == 0 && norm_rhs <= st->tol_r) {
-      st->done = 1;
-      st->termination = 0;
-      st->reason = 2;
-    }
-  }
-}
-
-// z = M^-1 r ; rho = r.z ; p = z (+ beta p) ; q = Df^2 p (seed of the S*p accumulation)
-// precond: 0 identity, otherwise block-diagonal 9x9 inverse blocks in minv [81C].
-__global__ void __launch_bounds__(kVecThreads)
-    cg_pre_kernel(CgParams prm, int precond, const double* __restrict__ minv, const double* __restrict__ Df,
-                  int seed_with_diagonal, const double* __restrict__ r, double* z, double* p, double* q, CgState* st) {
-  __shared__ double scratch[32];
-  __shared__ double s_beta;
-  __shared__ int s_stop;
-  if (st->done) return;
-  const int it = st->iteration + 1;
-  double acc = 0.0;
-  for (int i = threadIdx.x; i < prm.n; i += blockDim.x) {
-    double zi;
-    if (precond == 0) {
-      zi = r[i];
-    } else {
-      const int c = i / 9, row = i - 9 * c;
-      const double* m = minv + 81 * static_cast<size_t>(c) + 9 * row;
-      const double* rc = r + 9 * static_cast<size_t>(c);
-      zi = 0.0;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) zi += m[k] * rc[k];
-    }
-    z[i] = zi;
-    acc += r[i] * zi;
-  }
-  const double rho = block_sum<kVecThreads>(acc, scratch);
-  if (threadIdx.x == 0) {
-    s_stop = 0;
-    s_beta = 0.0;
-    const double last_rho = st->rho;
-    if (zero_or_inf(rho) || isnan(rho)) {
-      st->done = 1;
-      st->termination = 2;
-      st->reason = 4;
-      st->iteration = it;
-      s_stop = 1;
-    } else {
-      if (it > 1) {
-        const double beta = rho / last_rho;
-        if (zero_or_inf(beta)) {
-          st->done = 1;
-          st->termination = 2;
-          st->reason = 5;
-          st->iteration = it;
-          s_stop = 1;
-        }
-        s_beta = beta;
-      }
-      st->last_rho = last_rho;
-      st->rho = rho;
-      st->iteration = it;
-    }
-  }
-  __syncthreads();
-  if (s_stop) return;
-  const double beta = s_beta;
-  for (int i = threadIdx.x; i < prm.n; i += blockDim.x) {
-    const double pi = (it == 1) ? z[i] : z[i] + beta * p[i];
-    p[i] = pi;
-    q[i] = (seed_with_diagonal && Df != nullptr) ? Df[i] * Df[i] * pi : 0.0;
-  }
-}
-
-// mode 0: alpha = rho / p.q ; x += alpha p ; r -= alpha q ; then the termination tests
-// mode 1: alpha, x += alpha p only            (first half of a residual-reset iteration)
-// mode 2: r = rhs - Sx (sx given) ; then the termination tests   (second half)
-__global__ void __launch_bounds__(kVecThreads)
-    cg_post_kernel(CgParams prm, int mode, const double* __restrict__ rhs, const double* __restrict__ sx, double* x,
-                   double* r, const double* __restrict__ p, const double* __restrict__ q, CgState* st) {
-  __shared__ double scratch[32];
-  __shared__ double s_alpha;
-  __shared__ int s_stop;
-  if (st->done) return;
-  const int it = st->iteration;
-  if (mode != 2) {
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < prm.n; i += blockDim.x) acc += p[i] * q[i];
-    const double pq = block_sum<kVecThreads>(acc, scratch);
-    if (threadIdx.x == 0) {
-      s_stop = 0;
-      s_alpha = 0.0;
-      st->pq = pq;
-      if (!(pq > 0.0) || isinf(pq)) {  // (pq <= 0) || isinf(pq); NaN also lands here
-        st->done = 1;
-        st->termination = isnan(pq) ? 2 : 1;
-        st->reason = 6;
-        s_stop = 1;
-      } else {
-        const double alpha = st->rho / pq;
-        if (isinf(alpha)) {
-          st->done = 1;
-          st->termination = 2;
-          st->reason = 7;
-          s_stop = 1;
-        }
-        st->alpha = alpha;
-        s_alpha = alpha;
-      }
-    }
-    __syncthreads();
-    if (s_stop) return;
-  }
-  const double alpha = (mode != 2) ? s_alpha : 0.0;
-  double accQ = 0.0, accR = 0.0;
-  for (int i = threadIdx.x; i < prm.n; i += blockDim.x) {
-    double xi = x[i];
-    double ri = r[i];
-    if (mode != 2) {
-      xi += alpha * p[i];
-      x[i] = xi;
-    }
-    if (mode == 0) {
-      ri -= alpha * q[i];
-      r[i] = ri;
-    } else if (mode == 2) {
-      ri = rhs[i] - sx[i];
-      r[i] = ri;
-    }
-    accQ += xi * (rhs[i] + ri);
-    accR += ri * ri;
-  }
-  if (mode == 1) return;
-  const double dotQ = block_sum<kVecThreads>(accQ, scratch);
-  const double sqR = block_sum<kVecThreads>(accR, scratch);
-  if (threadIdx.x == 0) {
-    const double Q1 = -dotQ;
-    const double zeta = it * (Q1 - st->Q0) / Q1;
-    const double norm_r = sqrt(sqR);
-    st->norm_r = norm_r;
-    if (zeta < prm.q_tolerance && it >= prm.min_iterations) {
-      st->done = 1;
-      st->termination = 0;
-      st->reason = 1;
-    } else {
-      st->Q0 = Q1;
-      if (norm_r <= st->tol_r && it >= prm.min_iterations) {
-        st->done = 1;
-        st->termination = 0;
-        st->reason = 2;
-      } else if (it >= prm.max_iterations) {
-        st->done = 1;
-        st->termination = 1;
-        st->reason = 3;
-      }
-    }
-  }
-}
 
 // y[i] = d[i]^2 * x[i]  (or 0 when d == nullptr)
 __global__ void __launch_bounds__(256) diag_sq_mul_kernel(int n, const double* __restrict__ d,
