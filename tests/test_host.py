@@ -41,6 +41,28 @@ def test_struct_layouts_match_header(cs):
     assert lm.min_lm_diagonal == 1e-6 and lm.max_lm_diagonal == 1e32 and lm.linear_solver.max_num_iterations == 500
 
 
+def test_struct_sizes_match_a_c_compiler(cs, tmp_path):
+    """sizeof of every ABI struct as gcc sees include/b200ba.h against the ctypes mirrors in binding.py, plus the new
+    option fields' defaults (a silent layout mismatch would corrupt options, not crash)."""
+    import subprocess
+    from ceres_solver_b200 import binding as b
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "b200ba.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", '
+                   'sizeof(b200_ba_desc), sizeof(b200_solver_options), sizeof(b200_solver_summary), sizeof(b200_lm_options), '
+                   'sizeof(b200_lm_iteration), sizeof(b200_kernel_stat)); return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(t) for t in subprocess.check_output([str(exe)]).split()]
+    mirrors = [b.BaDesc, b.SolverOptions, b.SolverSummary, b.LmOptions, b.LmIteration, b.KernelStat]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+    o = b.SolverOptions()
+    cs.lib().b200_solver_options_default(ctypes.byref(o))
+    assert (o.max_num_spse_iterations, o.use_spse_initialization, o.spse_tolerance) == (5, 0, 0.1)
+    lm = b.LmOptions()
+    cs.lib().b200_lm_options_default(ctypes.byref(lm))
+    assert lm.linear_solver_type == cs.ITERATIVE_SCHUR and lm.linear_solver.spse_tolerance == 0.1
+
+
 def test_no_gpu_means_loud_failure_not_fallback(cs):
     import torch
     if torch.cuda.is_available():
