@@ -343,6 +343,11 @@ def test_ragged_structure_and_duplicates(cs, oracle):
     xg, its, term = case.gpu.schur_solve(b, D, case.gpu.solver_options(q_tolerance=1e-3, r_tolerance=-1.0))
     assert (its, term) == (its_o, term_o)
     assert relerr(xg, x_o) < 1e-8
+    # the explicit reduced camera system sees the duplicate as a block and its transpose on the diagonal
+    xd_o, _, _ = J.linear_solve(case.gpu.P, b, D, solver=1)
+    xd, _, termd = case.gpu.dense_schur_solve(b, D)
+    assert termd == cs.LS_SUCCESS
+    assert relerr(xd, xd_o) < 1e-8
 
 
 def _project(cameras, points, cam_idx, pt_idx):
