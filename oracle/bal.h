@@ -194,6 +194,55 @@ struct BalProblem {
   }
 };
 
+// HuberLoss::Evaluate (loss_function.cc:52-66): rho = {rho(s), rho'(s), rho''(s)}, s = squared residual norm.
+inline void HuberLossEvaluate(double a, double s, double rho[3]) {
+  const double b = a * a;  // loss_function.h: HuberLoss(a): a_(a), b_(a * a)
+  if (s > b) {
+    const double r = std::sqrt(s);
+    rho[0] = 2.0 * a * r - b;
+    rho[1] = std::max(std::numeric_limits<double>::min(), a / r);
+    rho[2] = -rho[1] / (2.0 * s);
+  } else {
+    rho[0] = s;
+    rho[1] = 1.0;
+    rho[2] = 0.0;
+  }
+}
+
+// Corrector (corrector.cc:41-155): rescales residuals and Jacobian so that the Gauss-Newton step of the corrected
+// problem is the robustified one.
+struct Corrector {
+  double sqrt_rho1, residual_scaling, alpha_sq_norm;
+  Corrector(double sq_norm, const double rho[3]) {
+    sqrt_rho1 = std::sqrt(rho[1]);
+    if (sq_norm == 0.0 || rho[2] <= 0.0) {  // :89-113
+      residual_scaling = sqrt_rho1;
+      alpha_sq_norm = 0.0;
+      return;
+    }
+    const double D = 1.0 + 2.0 * sq_norm * rho[2] / rho[1];
+    const double alpha = 1.0 - std::sqrt(D);
+    residual_scaling = sqrt_rho1 / (1 - alpha);
+    alpha_sq_norm = alpha / sq_norm;
+  }
+  void CorrectResiduals(int num_rows, double* residuals) const {  // :115-123
+    for (int r = 0; r < num_rows; ++r) residuals[r] *= residual_scaling;
+  }
+  // jacobian: num_rows x num_cols row-major; residuals: the UNCORRECTED ones (:125-155)
+  void CorrectJacobian(int num_rows, int num_cols, const double* residuals, double* jacobian) const {
+    if (alpha_sq_norm == 0.0) {
+      for (int k = 0; k < num_rows * num_cols; ++k) jacobian[k] *= sqrt_rho1;
+      return;
+    }
+    for (int c = 0; c < num_cols; ++c) {
+      double r_transpose_j = 0.0;
+      for (int r = 0; r < num_rows; ++r) r_transpose_j += jacobian[r * num_cols + c] * residuals[r];
+      for (int r = 0; r < num_rows; ++r)
+        jacobian[r * num_cols + c] = sqrt_rho1 * (jacobian[r * num_cols + c] - alpha_sq_norm * residuals[r] * r_transpose_j);
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------- BA program
 struct BaProgram {
   int C = 0, P = 0, N = 0;
@@ -315,49 +364,15 @@ struct BaProgram {
       *cost = 0.5 * squared_norm;
     } else {
       double rho[3];
-      const double b_ = huber_a * huber_a;  // loss_function.h: HuberLoss(a): a_(a), b_(a*a)
-      if (squared_norm > b_) {
-        const double rr = std::sqrt(squared_norm);
-        rho[0] = 2.0 * huber_a * rr - b_;
-        rho[1] = std::max(std::numeric_limits<double>::min(), huber_a / rr);
-        rho[2] = -rho[1] / (2.0 * squared_norm);
-      } else {
-        rho[0] = squared_norm;
-        rho[1] = 1.0;
-        rho[2] = 0.0;
-      }
+      HuberLossEvaluate(huber_a, squared_norm, rho);
       *cost = 0.5 * rho[0];
       if (jac_cam != nullptr || residuals != nullptr) {
-        // Corrector (corrector.cc:41-155)
-        const double sqrt_rho1 = std::sqrt(rho[1]);
-        double residual_scaling, alpha_sq_norm;
-        if (squared_norm == 0.0 || rho[2] <= 0.0) {
-          residual_scaling = sqrt_rho1;
-          alpha_sq_norm = 0.0;
-        } else {
-          const double Dd = 1.0 + 2.0 * squared_norm * rho[2] / rho[1];
-          const double alpha = 1.0 - std::sqrt(Dd);
-          residual_scaling = sqrt_rho1 / (1 - alpha);
-          alpha_sq_norm = alpha / squared_norm;
-        }
+        const Corrector correct(squared_norm, rho);   // residual_block.cc:170-195
         if (jac_cam != nullptr) {
-          auto correct = [&](double* jac, int num_cols) {
-            if (alpha_sq_norm == 0.0) {
-              for (int k = 0; k < 2 * num_cols; ++k) jac[k] *= sqrt_rho1;
-              return;
-            }
-            for (int c = 0; c < num_cols; ++c) {
-              double r_transpose_j = 0.0;
-              for (int rr = 0; rr < 2; ++rr) r_transpose_j += jac[rr * num_cols + c] * res[rr];
-              for (int rr = 0; rr < 2; ++rr)
-                jac[rr * num_cols + c] = sqrt_rho1 * (jac[rr * num_cols + c] - alpha_sq_norm * res[rr] * r_transpose_j);
-            }
-          };
-          correct(jac_cam, 9);
-          correct(jac_pt, 3);
+          correct.CorrectJacobian(2, 9, res, jac_cam);
+          correct.CorrectJacobian(2, 3, res, jac_pt);
         }
-        res[0] *= residual_scaling;
-        res[1] *= residual_scaling;
+        correct.CorrectResiduals(2, res);
       }
     }
     if (residuals != nullptr) {

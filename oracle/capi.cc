@@ -240,6 +240,40 @@ void orc_linear_solve_spse(void* h, int num_elim, int solver, int preconditioner
   out_summary[1] = s.termination_type;
 }
 
+// ------------------------------------------------------------------ ConjugateGradientsSolver on a dense symmetric matrix
+// (conjugate_gradients_solver_test.cc): identity preconditioner, x is the initial guess and the result.
+// out_summary = {num_iterations, termination_type}.
+void orc_cg_dense(int n, const double* A_rowmajor, const double* b, double* x, int min_iter, int max_iter,
+                  int residual_reset_period, double q_tolerance, double r_tolerance, int* out_summary) {
+  CGOptions o;
+  o.min_num_iterations = min_iter;
+  o.max_num_iterations = max_iter;
+  o.residual_reset_period = residual_reset_period;
+  o.q_tolerance = q_tolerance;
+  o.r_tolerance = r_tolerance;
+  std::vector<double> rhs(b, b + n), sol(x, x + n);
+  auto lhs = [&](const double* xx, double* yy) {
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) yy[i] += A_rowmajor[i * n + j] * xx[j];
+  };
+  auto identity = [&](const double* rr, double* zz) {
+    for (int i = 0; i < n; ++i) zz[i] += rr[i];
+  };
+  LinearSummary s = ConjugateGradients(o, lhs, rhs, identity, sol);
+  for (int i = 0; i < n; ++i) x[i] = sol[i];
+  out_summary[0] = s.num_iterations;
+  out_summary[1] = s.termination_type;
+}
+
+// ------------------------------------------------------------------ loss / corrector (for the known-answer tests)
+void orc_huber_loss(double a, double s, double* rho3) { HuberLossEvaluate(a, s, rho3); }
+// residuals [num_rows] and jacobian [num_rows x num_cols] are corrected in place (Jacobian first, like ResidualBlock::Evaluate)
+void orc_corrector(double sq_norm, const double* rho3, int num_rows, int num_cols, double* residuals, double* jacobian) {
+  const Corrector c(sq_norm, rho3);
+  if (jacobian != nullptr) c.CorrectJacobian(num_rows, num_cols, residuals, jacobian);
+  c.CorrectResiduals(num_rows, residuals);
+}
+
 // ------------------------------------------------------------------ BAL problem
 void* orc_bal_read(const char* path) {
   auto* p = new BalProblem;

@@ -174,6 +174,32 @@ class BlockSparseMatrix:
         return x, int(summ[0]), int(summ[1])
 
 
+def cg_dense(A, b, x0, min_iter=0, max_iter=500, reset_period=10, q_tolerance=0.0, r_tolerance=0.0):
+    """The oracle's ConjugateGradientsSolver on a dense symmetric matrix with the identity preconditioner."""
+    A = _f64(A)
+    x = _f64(x0).copy()
+    summ = np.zeros(2, dtype=np.int32)
+    lib().orc_cg_dense(A.shape[0], _d(A), _d(_f64(b)), _d(x), min_iter, max_iter, reset_period, C.c_double(q_tolerance),
+                       C.c_double(r_tolerance), _i(summ))
+    return x, int(summ[0]), int(summ[1])
+
+
+def huber_loss(a, s):
+    rho = np.zeros(3)
+    lib().orc_huber_loss(C.c_double(a), C.c_double(s), _d(rho))
+    return rho
+
+
+def corrector(sq_norm, rho, residuals, jacobian=None):
+    """Corrector(sq_norm, rho).CorrectJacobian + CorrectResiduals; returns the corrected copies."""
+    r = _f64(residuals).copy()
+    J = None if jacobian is None else _f64(jacobian).copy()
+    rows = r.size
+    cols = 0 if J is None else J.size // rows
+    lib().orc_corrector(C.c_double(sq_norm), _d(_f64(rho)), rows, cols, _d(r), _d(J))
+    return r, J
+
+
 class ImplicitSchur:
     def __init__(self, A, num_elim, want_ftf=False, nt=1, force_dynamic=0):
         self.A = A

@@ -314,3 +314,63 @@ def test_schur_jacobi_diagonal_matches_full(oracle):
         assert np.allclose(diag[p:p + s * s].reshape(s, s), lhs[c0:c0 + s, c0:c0 + s], rtol=1e-14)
         p += s * s
         c0 += s
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conjugate_gradients_solver_test.cc, loss_function_test.cc (HuberLoss), corrector_test.cc
+# ---------------------------------------------------------------------------------------------------------------------
+def test_cg_solves_3x3_identity_system(oracle):
+    """conjugate_gradients_solver_test.cc:47-87: A = I, b = (1, 2, 3), x0 = (1, 1, 1): one iteration, exact."""
+    x, its, term = oracle.cg_dense(np.eye(3), [1.0, 2.0, 3.0], [1.0, 1.0, 1.0], min_iter=1, max_iter=10,
+                                   reset_period=20, q_tolerance=0.0, r_tolerance=1e-9)
+    assert (term, its) == (0, 1)
+    assert np.array_equal(x, [1.0, 2.0, 3.0])
+
+
+def test_cg_solves_3x3_symmetric_system(oracle):
+    """:89-147: the tridiagonal [2 -1 0; -1 2 -1; 0 -1 2], b = (-1, 0, 3), x0 = (1, 1, 1) -> (0, 1, 2)."""
+    A = np.array([[2.0, -1.0, 0.0], [-1.0, 2.0, -1.0], [0.0, -1.0, 2.0]])
+    x, its, term = oracle.cg_dense(A, [-1.0, 0.0, 3.0], [1.0, 1.0, 1.0], min_iter=1, max_iter=10, reset_period=20,
+                                   q_tolerance=0.0, r_tolerance=1e-9)
+    assert term == 0
+    assert np.allclose(x, [0.0, 1.0, 2.0], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("a", [0.7, 1.3])
+@pytest.mark.parametrize("s", [0.357, 1.792])
+def test_huber_loss_derivatives(oracle, a, s):
+    """loss_function_test.cc:45-102: rho' and rho'' against symmetric finite differences of rho (h = 1e-4, 1e-6)."""
+    h = 1e-4
+    rho, fwd, bwd = oracle.huber_loss(a, s), oracle.huber_loss(a, s + h), oracle.huber_loss(a, s - h)
+    assert abs((fwd[0] - bwd[0]) / (2 * h) - rho[1]) < 1e-6
+    assert abs((fwd[0] - 2 * rho[0] + bwd[0]) / (h * h) - rho[2]) < 1e-6
+    assert np.allclose(oracle.huber_loss(0.7, 0.0), [0.0, 1.0, 0.0], atol=1e-6)
+
+
+@pytest.mark.parametrize("residual,rho", [(np.sqrt(3.0), [3.0, 0.1, -0.01]), (0.0, [0.0, 0.1, -0.01]),
+                                          (np.sqrt(3.0), [3.0, 0.1, -0.1])])
+def test_corrector_scalar_cases(oracle, residual, rho):
+    """corrector_test.cc:56-138: rho'' < 0 (or a zero residual) clamps alpha to 0: both scale by sqrt(rho')."""
+    r, J = oracle.corrector(residual * residual, rho, [residual], [10.0])
+    assert abs(r[0] - residual * np.sqrt(rho[1])) < 1e-6
+    assert abs(J[0] - np.sqrt(rho[1]) * 10.0) < 1e-6
+
+
+def test_corrector_multidimensional_gauss_newton(oracle):
+    """corrector_test.cc:140-205: corrected residuals / Jacobian against the closed forms and the robustified gradient."""
+    rng = np.random.RandomState(0)
+    for _ in range(2000):
+        jac = rng.uniform(0.0, 1.0, (3, 2))
+        res = rng.uniform(0.0, 1.0, 3)
+        sq = float(res @ res)
+        rho = [sq, rng.uniform(0.0, 1.0), rng.uniform(-1.0, 1.0)]
+        kD = 1 + 2 * rho[2] / rho[1] * sq
+        alpha = 1 - np.sqrt(kD) if rho[2] > 0.0 else 0.0
+        g_res = np.sqrt(rho[1]) / (1.0 - alpha) * res
+        g_jac = np.sqrt(rho[1]) * (jac - alpha / sq * np.outer(res, res) @ jac)
+        g_grad = rho[1] * jac.T @ res
+        r, J = oracle.corrector(sq, rho, res, jac)
+        J = J.reshape(3, 2)
+        assert np.linalg.norm(g_res - r) < 1e-10
+        assert np.linalg.norm(g_jac - J) < 1e-10
+        assert np.linalg.norm(g_grad - J.T @ r) < 1e-10
