@@ -147,3 +147,66 @@ def test_shard_partition_covers_all_rows():
             assert np.all(rp.row_pt[rlo:rhi] >= lo) and np.all(rp.row_pt[rlo:rhi] < hi)
             rows += rhi - rlo
         assert prev_hi == rp.P and rows == rp.N
+
+
+def _random_bal(rng, C, P, max_deg):
+    from ceres_solver_b200 import bal as B
+    cam, pt = [], []
+    for k in range(P):
+        d = rng.randint(1, min(max_deg, C) + 1)
+        cs_k = rng.choice(C, size=d, replace=False)
+        cam.extend(cs_k.tolist())
+        pt.extend([k] * d)
+    order = rng.permutation(len(cam))               # BAL files are not required to be grouped by point
+    cam = np.asarray(cam, dtype=np.int32)[order]
+    pt = np.asarray(pt, dtype=np.int32)[order]
+    obs = rng.normal(0.0, 100.0, (cam.size, 2))
+    cameras = rng.normal(0.0, 1.0, (C, 9))
+    points = rng.normal(0.0, 1.0, (P, 3))
+    return B.Bal(cam, pt, obs, cameras, points)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_reduced_program_invariants_on_random_structures(seed, tmp_path):
+    """Whatever the observation order of the input: rows grouped by point (the SchurEliminator precondition), points in
+    first-use order, a bijection between input observations and rows, BAL write/read round trip, and a shard partition
+    that is contiguous, complete and balanced to within one point's worth of rows."""
+    from ceres_solver_b200 import bal as B
+    rng = np.random.RandomState(100 + seed)
+    bal = _random_bal(rng, C=int(rng.randint(2, 12)), P=int(rng.randint(1, 60)), max_deg=int(rng.randint(1, 9)))
+    path = str(tmp_path / "p.txt")
+    B.write_bal(bal, path)
+    back = B.read_bal(path)
+    assert np.array_equal(back.cam_idx, bal.cam_idx) and np.array_equal(back.pt_idx, bal.pt_idx)
+    assert np.allclose(back.obs, bal.obs, rtol=1e-15, atol=0) and np.allclose(back.cameras, bal.cameras, rtol=1e-15, atol=0)
+    rp = B.ReducedProgram(bal)
+    # parameter blocks nobody observes are not part of the reduced program (Program::RemoveFixedBlocks drops them)
+    assert rp.N == bal.N and rp.P == np.unique(bal.pt_idx).size and rp.C == np.unique(bal.cam_idx).size
+    assert np.all(np.diff(rp.row_pt) >= 0)                       # grouped by (reduced) point
+    deg = np.bincount(rp.row_pt, minlength=rp.P)
+    assert deg.min() >= 1 and deg.sum() == rp.N
+    # every row is one input observation: same (original camera, original point, observation)
+    o = rp.obs_of_row
+    assert np.array_equal(np.sort(o), np.arange(bal.N))
+    assert np.array_equal(rp.camera_of_fblock[rp.row_cam], bal.cam_idx[o])
+    assert np.array_equal(rp.point_of_eblock[rp.row_pt], bal.pt_idx[o])
+    assert np.array_equal(rp.row_obs, bal.obs[o])
+    # parameter blocks in first-use order, rows of a point in reverse input order (SURVEY Appendix A)
+    first_pt = [int(np.flatnonzero(bal.pt_idx == p)[0]) for p in rp.point_of_eblock]
+    assert first_pt == sorted(first_pt)
+    first_cam = [int(np.flatnonzero(bal.cam_idx == c)[0]) for c in rp.camera_of_fblock]
+    assert first_cam == sorted(first_cam)
+    for k in range(rp.P):
+        rows = o[rp.row_pt == k]
+        assert np.all(np.diff(rows) < 0) or rows.size == 1
+    st = rp.state(bal)
+    assert st.size == 3 * rp.P + 9 * rp.C
+    for world in (1, 2, 3, 5):
+        covered_pts, covered_rows, sizes = 0, 0, []
+        for r in range(world):
+            lo, hi, rlo, rhi = rp.shard(r, world)
+            assert lo == covered_pts and rlo == covered_rows
+            covered_pts, covered_rows = hi, rhi
+            sizes.append(rhi - rlo)
+        assert covered_pts == rp.P and covered_rows == rp.N
+        assert max(sizes) - min(sizes) <= 2 * deg.max() + rp.N // world
