@@ -1,4 +1,4 @@
-"""world_size-2 (gloo, CPU) check of the multi-GPU decomposition: points are sharded by observation
+"""world_size-2 and -4 (gloo, CPU) check of the multi-GPU decomposition: points are sharded by observation
 count, cameras replicated, and every camera-sized quantity of the Schur path is the SUM over shards — so a single
 all-reduce of the 9C vector per CG iteration reproduces the unsharded product.  The per-shard arithmetic here is the
 CPU oracle's; the same partition function (ReducedProgram.shard) and the same id/all-reduce plumbing drive the GPU
@@ -74,7 +74,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_sharded_schur_product_is_a_sum_over_shards(world, tmp_path, oracle):
     import torch.multiprocessing as mp
     port = 29500 + (os.getpid() % 500)
