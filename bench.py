@@ -240,6 +240,31 @@ def main():
     stats = gpu.stats()
     gpu.profile(False)
     peak, peak_src = load_peaks()
+    # the other kernel BASELINE.json's metric names, J'J x (+ D^2 x) in one pass (not on the ITERATIVE_SCHUR path, so it
+    # is timed on its own: a few launches through the public entry point, kernel time from the same CUDA-event stats)
+    jtj = None
+    if world == 1:
+        try:
+            rng = np.random.RandomState(1)
+            xj = rng.randn(gpu.num_parameters)
+            Dj = np.abs(rng.randn(gpu.num_parameters)) + 0.1
+            gpu.jtj_multiply(xj, Dj)
+            gpu.stats_reset()
+            gpu.profile(True)
+            for _ in range(5):
+                gpu.jtj_multiply(xj, Dj)
+            sj = gpu.stats().get("jtj_multiply")
+            if sj and sj["ms"] > 0 and sj["launches"] > 0:
+                gbps = sj["bytes_per_launch"] * sj["launches"] / (sj["ms"] * 1e-3) / 1e9
+                jtj = {"GBps": round(gbps, 1), "frac": round(gbps / peak, 4), "launches": sj["launches"],
+                       "mean_launch_ms": round(sj["ms"] / sj["launches"], 4), "bytes_per_launch": sj["bytes_per_launch"]}
+        except Exception as e:  # never let the extra measurement take the bench line down
+            jtj = {"error": str(e)[:200]}
+        finally:
+            try:
+                gpu.profile(False)
+            except Exception:
+                pass
     total_ms = sum(v["ms"] for v in stats.values())
     by_time = max(((k, v) for k, v in stats.items() if v["bytes_per_launch"] > 0), key=lambda kv: kv[1]["ms"])[0]
     # the roofline line is about the kernel north_star names (the implicit-Schur product feeding CG), which is also
@@ -253,6 +278,13 @@ def main():
                    if v["ms"] > 0 and v["bytes_per_launch"] > 0 else None}
                for k, v in stats.items() if v["launches"] > 0}
 
+    # "Schur-eliminate" of the metric = (E'E + D^2)^-1, reduced rhs and the block diagonal of S (SCHUR_JACOBI)
+    elim = None
+    parts = [stats[k] for k in ("schur_init", "schur_diag_blocks") if stats.get(k, {}).get("launches", 0) > 0 and stats[k]["ms"] > 0]
+    if parts:
+        eb = sum(v["bytes_per_launch"] * v["launches"] for v in parts)
+        et = sum(v["ms"] for v in parts) * 1e-3
+        elim = {"GBps": round(eb / et / 1e9, 1), "frac": round(eb / et / 1e9 / peak, 4)}
     line = {"metric": METRIC, "value": iters / dev_s, "unit": UNIT, "n_gpus": world, "steps": iters,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / iters, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64",
@@ -271,6 +303,8 @@ def main():
                          "dominant_kernel_by_time": by_time,
                          "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},
             "kernels": kernels,
+            "jtj_multiply": jtj,
+            "schur_eliminate": elim,
             "final_cost": recs[-1]["cost"]}
     if world > 1:
         line["config"]["sharding"] = "points sharded over %d ranks by observation count, cameras replicated; one NCCL all-reduce of the %d-double camera vector per CG iteration" % (world, 9 * rp.C)
