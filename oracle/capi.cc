@@ -265,6 +265,11 @@ void orc_cg_dense(int n, const double* A_rowmajor, const double* b, double* x, i
   out_summary[1] = s.termination_type;
 }
 
+// ------------------------------------------------------------------ rotation (for the known-answer tests)
+void orc_angle_axis_rotate_point(const double* angle_axis, const double* pt, double* result) {
+  AngleAxisRotatePoint<double>(angle_axis, pt, result);
+}
+
 // ------------------------------------------------------------------ loss / corrector (for the known-answer tests)
 void orc_huber_loss(double a, double s, double* rho3) { HuberLossEvaluate(a, s, rho3); }
 // residuals [num_rows] and jacobian [num_rows x num_cols] are corrected in place (Jacobian first, like ResidualBlock::Evaluate)

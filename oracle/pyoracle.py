@@ -184,6 +184,12 @@ def cg_dense(A, b, x0, min_iter=0, max_iter=500, reset_period=10, q_tolerance=0.
     return x, int(summ[0]), int(summ[1])
 
 
+def angle_axis_rotate_point(angle_axis, pt):
+    out = np.zeros(3)
+    lib().orc_angle_axis_rotate_point(_d(_f64(angle_axis)), _d(_f64(pt)), _d(out))
+    return out
+
+
 def huber_loss(a, s):
     rho = np.zeros(3)
     lib().orc_huber_loss(C.c_double(a), C.c_double(s), _d(rho))

@@ -374,3 +374,20 @@ def test_corrector_multidimensional_gauss_newton(oracle):
         assert np.linalg.norm(g_res - r) < 1e-10
         assert np.linalg.norm(g_jac - J) < 1e-10
         assert np.linalg.norm(g_grad - J.T @ r) < 1e-10
+
+
+def test_angle_axis_rotate_point_matches_rotation_matrix(oracle):
+    """rotation_test.cc:1809-1857 and :1873-1921 (tolerance 10 eps there; 1e-14 here, the comparison goes through scipy's
+    rotation matrix): AngleAxisRotatePoint against R(angle_axis) p for angles across (-pi, pi) and for the near-zero
+    branch (|theta| <= 1e-16, first-order Taylor expansion)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.RandomState(3)
+    thetas = np.concatenate([(2.0 * np.arange(0, 10000, 37) * 0.0011 - 1.0) * np.pi,
+                             (2.0 * np.arange(0, 10000, 97) * 0.0001 - 1.0) * 1e-16])
+    for theta in thetas:
+        axis = rng.uniform(-1.0, 1.0, 3)
+        p = rng.uniform(-1.0, 1.0, 3)
+        aa = axis * (theta / np.linalg.norm(axis))
+        expect = Rotation.from_rotvec(aa).as_matrix() @ p
+        got = oracle.angle_axis_rotate_point(aa, p)
+        assert np.abs(got - expect).max() < 1e-14
