@@ -565,8 +565,10 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
 // (E'E+D^2)^-1 blocks of its points and a 160-byte descriptor block (row words, the tile's own extents and the extents
 // of the tile that will reuse the ring slot) -- and x of the CTA's camera range is staged once in shared memory, so the
 // main loop issues no global load at all (ncu on v3, profiles/r01_v3_schur_mul_l1723_ncu.txt: a third of all stall
-// samples were long-scoreboard waits on the row word -> x -> (E'E)^-1 dependency chain).  With 12 warps per SM the
-// register budget is 168, so the F cells are read from shared memory once and stay in registers.
+// samples were long-scoreboard waits on the row word -> x -> (E'E)^-1 dependency chain).  The slot's contents go to
+// registers first (the F cells stay there, 36 registers; the kernel sits at 122-126 of the 128 registers that 16 warps
+// allow) and the slot is refilled at once, so one slot per warp is enough; with one private camera vector per warp the
+// accumulation needs no atomics (cam_accumulate9_owned).
 // ------------------------------------------------------------------------------------------------
 constexpr int kV4MaxThreads = 512;
 constexpr int kV4MetaWords = 40;
