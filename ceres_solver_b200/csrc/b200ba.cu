@@ -1701,6 +1701,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->mul_v4 = true;
         h->big_folded = getenv("B200_DISABLE_BIG_FOLD") == nullptr;
         h->mul_v4_owned = rep4 == w4;
+        CU(cudaFuncSetAttribute(jtj_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(jtj_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
@@ -2010,6 +2012,26 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
   const size_t off = 3 * static_cast<size_t>(h->P);
   const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
   const int nc = 9 * h->C;
+  if (h->mul_v4 && h->v2.direct && getenv("B200_JTJ_V4") != nullptr) {
+    // EXPERIMENTAL (not yet run on hardware, see jtj_v4_kernel): seed y = D^2 x everywhere, the tile kernel adds J'(J x)
+    OK(launch(h, K_MISC, [&] {
+      diag_sq_mul_kernel<<<flat_grid(h, off, 256), 256, 0, h->stream>>>(static_cast<int>(off), dD, h->d_vp0, h->d_vp1, nullptr);
+    }));
+    OK(launch(h, K_MISC, [&] {
+      diag_sq_mul_kernel<<<flat_grid(h, nc, 256), 256, 0, h->stream>>>(nc, seedD, h->d_vp0 + off, h->d_vp1 + off, nullptr);
+    }));
+    OK(huge_zero(h, h->d_vp1));  // the chunk tiles of huge points add their own D^2 x
+    OK(launch(h, K_JTJ, [&] {
+      if (h->mul_v4_owned) jtj_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_vp0, h->d_vp1);
+      else jtj_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_vp0, h->d_vp1);
+    }));
+    if (h->num_big_tiles > 0)
+      OK(launch(h, K_JTJ, [&] {
+        jtmul_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, h->d_vp0, dD, h->d_vp1);
+      }));
+    OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
+    return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
+  }
   OK(huge_zero(h, h->d_vp1));  // point entries of huge points are accumulated slice by slice
   if (h->v2_ok) {
     if (h->v2.direct)

@@ -858,6 +858,128 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
+// EXPERIMENTAL, opt-in (B200_JTJ_V4=1), written at the end of round 1 after the GPU budget was spent: NOT yet run on
+// hardware.  y += J'(J x) with the v4 machinery (the caller seeds y = D^2 x): the slot carries F, E, the descriptor
+// block and -- in the place of the (E'E)^-1 blocks -- the point part of x for the tile's points (24 B per point: the
+// bulk copy fetches the 16-byte-aligned superset, `xoff` is where the tile's first point starts inside it); x of the
+// camera range is staged like in S*x.  Per row t = E x_p + F x_c; the camera part F't goes through the per-warp private
+// vectors and the direct flush, the point part sum_rows E't is added to y with three REDs per point.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jtj_v4_issue(const V2View& v, const double* x, unsigned char* stage, uint64_t* bar, int tile,
+                                             int row_begin, int pt_begin, int row_count, int pt_count) {
+  const uint32_t xoff = (pt_begin & 1) ? 8u : 0u;                       // (24 * pt_begin) mod 16
+  const uint32_t xbytes = (24u * pt_count + xoff + 15u) & ~15u;         // <= 784
+  mbar_arrive_expect_tx(bar, row_count * 192u + xbytes + kV4MetaWords * 4u);
+  bulk_g2s(stage, v.p.F() + 18 * static_cast<size_t>(row_begin), row_count * 144u, bar);
+  bulk_g2s(stage + 4608, v.p.E() + 6 * static_cast<size_t>(row_begin), row_count * 48u, bar);
+  bulk_g2s(stage + 6144, reinterpret_cast<const unsigned char*>(x + 3 * static_cast<size_t>(pt_begin)) - xoff, xbytes, bar);
+  bulk_g2s(stage + 7680, v.tile_meta + static_cast<size_t>(kV4MetaWords) * tile, kV4MetaWords * 4u, bar);
+}
+
+template <bool kOwned>
+__global__ void __launch_bounds__(kV4MaxThreads, 1)
+    jtj_v4_kernel(V2View v, const double* __restrict__ x, double* y) {
+  const V4Ctx c = v4_ctx(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 part = c.part, cr = c.cr;
+  const size_t off = 3 * static_cast<size_t>(v.p.P);
+  v4_init(v, c);
+  if (lane == 0) {
+    int t = part.x + warp;
+    for (int s = 0; s < v.stages && t < part.y; ++s, t += v.warps) {
+      const WarpTile wt = v.wtiles[t];
+      jtj_v4_issue(v, x, c.wbase() + s * kV4StageBytes, c.bars() + s, t, wt.row_begin, wt.pt_begin, wt.row_count, wt.pt_count);
+    }
+  }
+  {
+    const int n = c.sy_stride * v.replicas;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) c.sy()[i] = 0.0;
+    const double* xs = x + off + 9 * static_cast<size_t>(cr.x);
+    for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) c.sx()[i] = __ldcg(xs + i);
+  }
+  __syncthreads();
+  const double* sx = c.sx();
+  double* sW = c.sW();
+  double* my_y = c.sy() + (kOwned ? warp : warp % v.replicas) * c.sy_stride;
+  const int reissue = v.warps * v.stages;
+  int it = 0;
+  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
+    const int s = it % v.stages;
+    const uint32_t parity = (it / v.stages) & 1u;
+    unsigned char* stage = c.wbase() + s * kV4StageBytes;
+    const double* sF = reinterpret_cast<const double*>(stage);
+    const double* sE = reinterpret_cast<const double*>(stage + 4608);
+    const uint32_t* sM = reinterpret_cast<const uint32_t*>(stage + 7680);
+    mbar_wait(c.bars() + s, parity);
+    const uint4 own = *reinterpret_cast<const uint4*>(sM + 32);
+    const uint4 nxt = *reinterpret_cast<const uint4*>(sM + 36);
+    const int row_count = static_cast<int>(own.z & 0xffffu);
+    const int pt_begin = static_cast<int>(own.y);
+    const bool active = lane < row_count;
+    const uint32_t meta = active ? sM[lane] : 0u;
+    const int cam = static_cast<int>(meta & 0x7fffffffu);
+    const Seg sg = v2_segment(active && (meta >> 31), row_count);
+    double f[18];
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    double xp0 = 0.0, xp1 = 0.0, xp2 = 0.0;
+    if (active) {
+      const double* fr = sF + lane * 18;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(fr + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+      e0 = lds2(sE + lane * 6);
+      e1 = lds2(sE + lane * 6 + 2);
+      e2 = lds2(sE + lane * 6 + 4);
+      const double* xp = reinterpret_cast<const double*>(stage + 6144 + ((pt_begin & 1) ? 8 : 0)) + 3 * sg.lpt;
+      xp0 = xp[0];
+      xp1 = xp[1];
+      xp2 = xp[2];
+    }
+    __syncwarp();  // every lane is done with the ring slot (and with the previous tile's scratch)
+    if (lane == 0 && (nxt.z & 0xffffu) != 0u)
+      jtj_v4_issue(v, x, stage, c.bars() + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
+                   static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
+    double t0 = 0.0, t1 = 0.0;
+    if (active) {
+      const double* xcp = sx + 9 * (cam - cr.x);
+      t0 = e0.x * xp0 + e0.y * xp1 + e1.x * xp2;
+      t1 = e1.y * xp0 + e2.x * xp1 + e2.y * xp2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double xk = xcp[k];
+        t0 += f[k] * xk;
+        t1 += f[9 + k] * xk;
+      }
+      sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
+      sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
+      sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+    }
+    __syncwarp();
+    if (active && lane == sg.first) {  // point part: sum over the rows of the point, added to the seeded y
+      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+      for (int j = sg.first; j < sg.end; ++j) {
+        u0 += sW[j * 3 + 0];
+        u1 += sW[j * 3 + 1];
+        u2 += sW[j * 3 + 2];
+      }
+      double* yp = y + 3 * static_cast<size_t>(pt_begin + sg.lpt);
+      red_add(yp, u0);
+      red_add(yp + 1, u1);
+      red_add(yp + 2, u2);
+    }
+    double g[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g[k] = active ? f[k] * t0 + f[9 + k] * t1 : 0.0;
+    if (kOwned) cam_accumulate9_owned(my_y, cam - cr.x, active, g);
+    else cam_accumulate9(my_y, cam - cr.x, active, g);
+  }
+  v2_epilogue(v, c.sy(), cr, y + off);
+}
+
+// ------------------------------------------------------------------------------------------------
 // y = J'(J x) + D^2 x in one pass: point part written directly (owned by the tile), camera part -> partials.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kV2MaxThreads, 1)
