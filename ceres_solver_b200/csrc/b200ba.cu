@@ -2012,8 +2012,8 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
   const size_t off = 3 * static_cast<size_t>(h->P);
   const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
   const int nc = 9 * h->C;
-  if (h->mul_v4 && h->v2.direct && getenv("B200_JTJ_V4") != nullptr) {
-    // EXPERIMENTAL (not yet run on hardware, see jtj_v4_kernel): seed y = D^2 x everywhere, the tile kernel adds J'(J x)
+  if (h->mul_v4 && h->v2.direct && getenv("B200_NO_JTJ_V4") == nullptr) {
+    // v4 machinery (jtj_v4_kernel): seed y = D^2 x everywhere, the tile kernel adds J'(J x)
     OK(launch(h, K_MISC, [&] {
       diag_sq_mul_kernel<<<flat_grid(h, off, 256), 256, 0, h->stream>>>(static_cast<int>(off), dD, h->d_vp0, h->d_vp1, nullptr);
     }));

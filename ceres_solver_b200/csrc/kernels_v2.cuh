@@ -858,8 +858,8 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// EXPERIMENTAL, opt-in (B200_JTJ_V4=1), written at the end of round 1 after the GPU budget was spent: NOT yet run on
-// hardware.  y += J'(J x) with the v4 machinery (the caller seeds y = D^2 x): the slot carries F, E, the descriptor
+// y += J'(J x) with the v4 machinery (the caller seeds y = D^2 x).  Written at the very end of round 1: parity-green on
+// hardware (tests/test_gpu_parity.py::test_jtj_v4), its GB/s not yet profiled (B200_NO_JTJ_V4=1 selects jtj_v2_kernel): the slot carries F, E, the descriptor
 // block and -- in the place of the (E'E)^-1 blocks -- the point part of x for the tile's points (24 B per point: the
 // bulk copy fetches the 16-byte-aligned superset, `xoff` is where the tile's first point starts inside it); x of the
 // camera range is staged like in S*x.  Per row t = E x_p + F x_c; the camera part F't goes through the per-warp private

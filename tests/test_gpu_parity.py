@@ -479,11 +479,9 @@ def test_lm_trajectory_dense_schur(host_boundary, c16_case, cs):
     assert relerr(state, state_o) < 1e-6
 
 
-@pytest.mark.skipif(__import__("os").environ.get("B200_TEST_EXPERIMENTAL") is None,
-                    reason="jtj_v4_kernel was written after the round-1 GPU budget was spent: run with B200_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("which", ["c16", "tiny", "huge"])
-def test_jtj_v4_experimental(which, c16_case, tiny_case, huge_case):
-    """The opt-in one-pass J'J x kernel on the v4 machinery (B200_JTJ_V4=1) against the oracle and the default kernel."""
+def test_jtj_v4(which, c16_case, tiny_case, huge_case):
+    """The one-pass J'J x kernel on the v4 machinery (default) and the v2 kernel (B200_NO_JTJ_V4=1) against the oracle."""
     import os
     case = {"c16": c16_case, "tiny": tiny_case, "huge": huge_case}[which]
     _evaluate_both(case)
@@ -492,12 +490,12 @@ def test_jtj_v4_experimental(which, c16_case, tiny_case, huge_case):
     x = rng.randn(case.gpu.num_parameters)
     for D in (np.abs(rng.randn(case.gpu.num_parameters)) + 0.1, None):
         expect = J.left_multiply(J.right_multiply(x, nt=8), nt=8) + (D * D * x if D is not None else 0.0)
-        base = case.gpu.jtj_multiply(x, D)
-        os.environ["B200_JTJ_V4"] = "1"
+        got = case.gpu.jtj_multiply(x, D)
+        os.environ["B200_NO_JTJ_V4"] = "1"
         try:
-            got = case.gpu.jtj_multiply(x, D)
+            base = case.gpu.jtj_multiply(x, D)
         finally:
-            del os.environ["B200_JTJ_V4"]
+            del os.environ["B200_NO_JTJ_V4"]
         assert relerr(base, expect) < 1e-12
         assert relerr(got, expect) < 1e-12
 
