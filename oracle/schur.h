@@ -8,6 +8,10 @@
 //   ConjugateGradients         internal/ceres/conjugate_gradients_solver.h:109-306
 //   IterativeSchurSolve        internal/ceres/iterative_schur_complement_solver.cc:64-157
 //   DenseSchurSolve            internal/ceres/schur_complement_solver.cc:101-159 (Dense variant)
+//   PowerSeriesExpansion       internal/ceres/power_series_expansion_preconditioner.cc:57-82,
+//                              implicit_schur_complement.cc:146-174
+// Parity: pinned (tests/test_oracle_kat.py, tests/test_oracle_ba.py: the reference's fixtures, known-answer tests and
+// published per-iteration transcripts).
 // Templated on <row, e, f> block sizes exactly like the reference
 // (schur_eliminator.cc:56-135 instantiations); kDyn == Eigen::Dynamic.
 #pragma once
