@@ -31,8 +31,6 @@
 #include "kernels_v2b.cuh"
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
-#include "pcg_kernel.cuh"
-#include "pcg_split.cuh"
 #include "spse_kernels.cuh"
 #include "huge_kernels.cuh"
 #include "dense_schur.cuh"
@@ -42,6 +40,14 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_error;
+
+// Development switches (A/B measurements of kernel variants and tuning knobs) exist only in builds with
+// -DB200_DEV_KNOBS; the product library has a single code path per problem class and reads no such variable.
+#ifdef B200_DEV_KNOBS
+inline const char* dev_env(const char* name) { return getenv(name); }
+#else
+inline const char* dev_env(const char*) { return nullptr; }
+#endif
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -82,7 +88,6 @@ enum KernelId {
   K_BACKSUB,
   K_MODEL_COST,
   K_CG_VEC,
-  K_PCG,
   K_LM_VEC,
   K_MISC,
   K_COUNT
@@ -90,7 +95,7 @@ enum KernelId {
 const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squared_column_norm", "scale_columns",
                                      "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
                                      "schur_multiply", "schur_multiply_big_points", "camera_reduce", "schur_diag_blocks", "invert_9x9", "back_substitute",
-                                     "model_cost", "cg_vector", "pcg_persistent", "lm_vector", "misc"};
+                                     "model_cost", "cg_vector", "lm_vector", "misc"};
 
 // cuSOLVER (dense Cholesky of the explicit reduced camera system) is bound lazily with dlopen like NCCL: the
 // library is only touched by b200_dense_schur_solve, and shares whatever libcusolver.so.11 the process already has.
@@ -248,17 +253,8 @@ struct b200_handle {
   uint32_t* d_tile_meta = nullptr;
   bool mul_v4 = false, mul_v4_owned = false;
   bool residuals_resident = false;  // d_residuals holds the residuals of the last b200_evaluate(..., residuals != NULL)
-  bool pcg_ok = false;       // the whole PCG runs as one persistent cooperative kernel (pcg_kernel.cuh)
-  int pcg_cams_per_cta = 0;
-  double *d_qa = nullptr, *d_qb = nullptr, *d_pcg_red = nullptr;
   double *d_ftf_inv = nullptr, *d_spse[3] = {nullptr, nullptr, nullptr};  // general-preconditioner PCG (SPSE)
-  bool split_ok = false;      // split-phase PCG (pcg_split.cuh): no grid-wide barrier anywhere in the iteration
-  int2* d_cta_own = nullptr;
-  CgState* d_cg3 = nullptr;   // [3] ping-pong slots + final summary
-  double* d_split_red = nullptr;
-  int split_grid = 0;
   double *d_pq_parts = nullptr, *d_seed_pq = nullptr;  // fused p.q: per-CTA partials of the product / of the vector kernel
-  unsigned* d_pcg_barrier = nullptr;
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
@@ -279,7 +275,6 @@ struct b200_handle {
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
   int cg_grid = 1;
-  int cg_cluster_cams = 0;   // > 0: cg_cluster_kernel with this many cameras per CTA replaces the cooperative kernel
   PinnedVec hv[12];           // host-boundary LM loop vectors
   // launch geometry
   int grid_tile[K_COUNT];
@@ -535,8 +530,7 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
     OK(launch(h, K_SCHUR_MUL, [&] {
       if (h->mul_v4 && h->mul_v4_owned) schur_mul_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag, nullptr);
       else if (h->mul_v4) schur_mul_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag, nullptr);
-      else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
-      else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, d_x, d_y, done_flag);
+      else schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, d_x, d_y, done_flag);
     }));
     if (!h->v2.direct)
       OK(launch(h, K_CAM_REDUCE, [&] {
@@ -661,10 +655,6 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     va.mode = mode;
     va.q = q;
     va.seed_target = seeded ? seed_target : nullptr;
-    if (h->cg_cluster_cams > 0)  // one 8-CTA cluster, cluster barriers instead of grid syncs
-      return launch(h, K_CG_VEC, [&] {
-        cg_cluster_kernel<<<kCgClusterSize, kCgClusterThreads, sizeof(double) * 9 * h->cg_cluster_cams, h->stream>>>(va, h->cg_cluster_cams);
-      });
     void* args[] = {&va};
     return launch(h, K_CG_VEC, [&] {
       cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
@@ -672,12 +662,12 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   };
   // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
   const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
-                       getenv("B200_NO_FUSED_PQ") == nullptr;
+                       dev_env("B200_NO_FUSED_PQ") == nullptr;
   double* pq_parts = fuse_pq ? h->d_pq_parts : nullptr;
   va.pq_parts = pq_parts;
   va.num_pq_parts = fuse_pq ? h->v2.num_ctas : 0;
   va.seed_pq = fuse_pq ? h->d_seed_pq : nullptr;
-  const bool use_pdl = getenv("B200_NO_PDL") == nullptr && !h->profiling;
+  const bool use_pdl = dev_env("B200_NO_PDL") == nullptr && !h->profiling;
   auto product = [&](const double* vin, double* out) -> int {
     if (seeded) {
       // The handful of >32-row points runs on a side stream, concurrently with the warp-tile kernel (both only add
@@ -708,8 +698,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
           if (h->mul_v4_owned) cudaLaunchKernelEx(&cfg, schur_mul_v4_kernel<true>, h->v2_mul, static_cast<const double*>(h->d_ete_inv), vin, out, done_ptr, pq_parts);
           else cudaLaunchKernelEx(&cfg, schur_mul_v4_kernel<false>, h->v2_mul, static_cast<const double*>(h->d_ete_inv), vin, out, done_ptr, pq_parts);
         }
-        else if (h->mul_v3) schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
-        else schur_mul_v2_kernel<<<h->v2.num_ctas, 32 * h->v2.warps, h->v2_smem, h->stream>>>(h->v2, h->d_ete_inv, vin, out, &h->d_cg->done);
+        else schur_mul_v3_kernel<<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, vin, out, &h->d_cg->done);
       }));
       if (side) {
         CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
@@ -727,165 +716,9 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
   };
-  if (h->pcg_ok && !h->profiling) {
-    // single persistent kernel: product, vector updates and termination tests of every iteration (pcg_kernel.cuh)
-    PcgArgs pa{};
-    pa.v = h->v2_mul;
-    pa.ete_inv = h->d_ete_inv;
-    pa.prm = prm;
-    pa.prm.max_iterations = std::max(o->max_num_iterations, 1);
-    pa.C = h->C;
-    pa.cams_per_cta = h->pcg_cams_per_cta;
-    pa.reset_period = o->residual_reset_period > 0 ? o->residual_reset_period : 0;
-    pa.precond = precond;
-    pa.Df = Df;
-    pa.minv = h->d_minv;
-    pa.rhs = h->d_rhs;
-    pa.x = h->d_sol;
-    pa.r = h->d_r;
-    pa.z = h->d_z;
-    pa.p = h->d_p;
-    pa.qa = h->d_qa;
-    pa.qb = h->d_qb;
-    pa.tmp = h->d_tmp;
-    pa.red = h->d_pcg_red;
-    pa.st = h->d_cg;
-    pa.barrier = h->d_pcg_barrier;
-    const char* trace_path = getenv("B200_PCG_TRACE");
-    const int trace_iters = 64;
-    unsigned long long* d_trace = nullptr;
-    if (trace_path != nullptr) {
-      OK(dev_alloc(&d_trace, static_cast<size_t>(h->v2.num_ctas) * trace_iters * 8));
-      CU(cudaMemsetAsync(d_trace, 0, sizeof(unsigned long long) * h->v2.num_ctas * trace_iters * 8, h->stream));
-      pa.trace = d_trace;
-      pa.trace_iters = trace_iters;
-    }
-    CU(cudaMemsetAsync(h->d_pcg_barrier, 0, 4 * sizeof(unsigned), h->stream));
-    void* args[] = {&pa};
-    OK(launch(h, K_PCG, [&] {
-      if (h->mul_v4_owned)
-        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pcg_kernel<true>), dim3(h->v2.num_ctas), dim3(32 * h->v2_mul.warps), args, h->mul_smem, h->stream);
-      else
-        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(pcg_kernel<false>), dim3(h->v2.num_ctas), dim3(32 * h->v2_mul.warps), args, h->mul_smem, h->stream);
-    }));
-    CU(cudaMemcpyAsync(h->h_cg, h->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (d_trace != nullptr) {  // debugging aid: phase time stamps of the first iterations, one file per solve (overwritten)
-      std::vector<unsigned long long> tr(static_cast<size_t>(h->v2.num_ctas) * trace_iters * 8);
-      CU(cudaMemcpy(tr.data(), d_trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      if (FILE* f = fopen(trace_path, "wb")) {
-        fwrite(tr.data(), sizeof(unsigned long long), tr.size(), f);
-        fclose(f);
-      }
-      cudaFree(d_trace);
-    }
-    return finish();
-  }
   if (general) {
     // power-series preconditioner / initial guess -> the general-preconditioner PCG (host-side scalars)
     OK(pcg_general_dev(h, o));
-    return finish();
-  }
-  if (h->split_ok) {
-    // split-phase PCG: vector kernel (alpha, x, r, z, partial sums) and product kernel (tests, beta, p, S0 p, p.q)
-    // alternate; neither needs a grid-wide barrier (pcg_split.cuh)
-    const int max_it = std::max(o->max_num_iterations, 1);
-    const int reset = o->residual_reset_period > 0 ? o->residual_reset_period : std::numeric_limits<int>::max();
-    if (h->d_pq_parts == nullptr) return fail(B200_ERR_CUDA, "split PCG buffers missing");
-    CgSplitArgs ca{};
-    ca.prm = prm;
-    ca.prm.max_iterations = max_it;
-    ca.C = h->C;
-    ca.st = h->d_cg3;
-    ca.Df = Df;
-    ca.precond = precond;
-    ca.minv = h->d_minv;
-    ca.rhs = h->d_rhs;
-    ca.x = h->d_sol;
-    ca.r = h->d_r;
-    ca.z = h->d_z;
-    ca.p = h->d_p;
-    ca.pq_parts = h->d_pq_parts;
-    ca.num_pq_parts = h->v2.num_ctas;
-    ca.red = h->d_split_red;
-    PcgLink L{};
-    L.st = h->d_cg3;
-    L.prm = ca.prm;
-    L.red = h->d_split_red;
-    L.red_n = h->split_grid;
-    L.z = h->d_z;
-    L.p = h->d_p;
-    L.xvec = h->d_sol;
-    L.Df = Df;
-    L.cta_own = h->d_cta_own;
-    L.pq_parts = h->d_pq_parts;
-    int slot = 0;
-    auto vecs = [&](int mode, const double* q, double* zero_a, double* zero_b) -> int {
-      ca.mode = mode;
-      ca.slot = slot;
-      ca.q = q;
-      ca.zero_a = zero_a;
-      ca.zero_b = zero_b;
-      return launch(h, K_CG_VEC, [&] { cg_split_kernel<<<h->split_grid, kSplitThreads, 0, h->stream>>>(ca); });
-    };
-    auto prod = [&](int mode, double* out) -> int {
-      L.mode = mode;
-      L.slot = slot;
-      OK(launch(h, K_SCHUR_MUL, [&] {
-        if (h->mul_v4_owned) schur_mul_v4_pcg_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, L, out);
-        else schur_mul_v4_pcg_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_ete_inv, L, out);
-      }));
-      if (mode != PM_RESET_X) slot = 1 - slot;
-      return B200_OK;
-    };
-    double* qbuf[2] = {h->d_qa, h->d_qb};
-    OK(vecs(CA_BEGIN, nullptr, h->d_qa, h->d_qb));
-    OK(prod(PM_FIRST, qbuf[1]));          // tests of the start state, p = z, S0 p of iteration 1
-    int it = 0;
-    auto batch = [&](int count) -> int {
-      for (int k = 0; k < count && it < max_it; ++k) {
-        ++it;
-        if (it % reset == 0) {
-          OK(vecs(CA_RESET_FIRST, nullptr, h->d_tmp, nullptr));
-          OK(prod(PM_RESET_X, h->d_tmp));
-          OK(vecs(CA_RESET_SECOND, h->d_tmp, qbuf[(it + 1) & 1], nullptr));
-        } else {
-          OK(vecs(CA_NORMAL, qbuf[it & 1], qbuf[(it + 1) & 1], nullptr));
-        }
-        OK(prod(PM_NORMAL, qbuf[(it + 1) & 1]));   // tests of iteration `it`, then S0 p of iteration it + 1
-      }
-      return B200_OK;
-    };
-    const CgState* d_final = h->d_cg3 + 2;
-    if (h->profiling) {
-      bool done = false;
-      while (!done) {
-        OK(batch(1));
-        CU(cudaMemcpyAsync(h->h_cg, d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        done = h->h_cg->done != 0 || it >= max_it;
-      }
-      return finish();
-    }
-    int check_every = 2, pending = 0;
-    OK(batch(check_every));
-    CU(cudaMemcpyAsync(h->h_cg + pending, d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaEventRecord(h->ev_cg[pending], h->stream));
-    for (;;) {
-      const bool more = it < max_it;
-      if (more) {
-        check_every = std::min(check_every * 2, 8);
-        OK(batch(check_every));
-        CU(cudaMemcpyAsync(h->h_cg + (1 - pending), d_final, sizeof(CgState), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaEventRecord(h->ev_cg[1 - pending], h->stream));
-      }
-      CU(cudaEventSynchronize(h->ev_cg[pending]));
-      if (h->h_cg[pending].done != 0 || !more) {
-        if (pending != 0) h->h_cg[0] = h->h_cg[pending];
-        break;
-      }
-      pending = 1 - pending;
-    }
     return finish();
   }
   OK(vec(CG_BEGIN, h->d_z, h->d_z));
@@ -1342,7 +1175,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   std::vector<WarpTile> wtiles;
   std::vector<TileDesc> big_tiles;
   std::vector<uint32_t> row_meta(static_cast<size_t>(N));
-  bool v2_possible = getenv("B200_DISABLE_V2") == nullptr;
+  bool v2_possible = dev_env("B200_DISABLE_V2") == nullptr;
   for (int k = 0; k < P && v2_possible; ++k)
     if (pt_ptr[k + 1] == pt_ptr[k]) v2_possible = false;
   if (v2_possible) {
@@ -1394,7 +1227,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     const int T = static_cast<int>(wtiles.size());
     {
       double big_cost = 22.0;
-      if (const char* e = getenv("B200_BIG_COST")) big_cost = std::max(0.0, atof(e));
+      if (const char* e = dev_env("B200_BIG_COST")) big_cost = std::max(0.0, atof(e));
       const double total_cost = T + big_cost * big_tiles.size();
       int t = 0, g = 0, b = 0;
       double cum = 0.0;
@@ -1463,15 +1296,15 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     choose(kV2MaxThreads / 32, 3, &v2_warps, &v2_stages, &v2_replicas);
     // the S*x kernel runs under 128 registers: up to 16 warps, 2-deep ring
     choose(kV3MaxThreads / 32, 2, &mul_warps, &mul_stages, &mul_replicas);
-    if (const char* e = getenv("B200_V3_WARPS")) {  // tuning knob
+    if (const char* e = dev_env("B200_V3_WARPS")) {  // tuning knob
       const int w = atoi(e);
       if (w >= 1 && w <= mul_warps) { mul_warps = w; mul_replicas = std::min(mul_replicas, w); }
     }
-    if (const char* e = getenv("B200_V3_REPLICAS")) {
+    if (const char* e = dev_env("B200_V3_REPLICAS")) {
       const int r = atoi(e);
       if (r >= 1 && r <= mul_replicas) mul_replicas = r;
     }
-    if (v2_warps == 0) v2_possible = false;  // camera vector does not fit next to the tile buffers: v1 kernels
+    if (v2_warps == 0 || mul_warps == 0) v2_possible = false;  // camera vector does not fit next to the tile buffers: v1 kernels
   } else {
     v2_possible = false;
   }
@@ -1580,7 +1413,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->view.obs = h->d_obs;
   h->view.values = h->d_values;
 
-  if (!has_dups && getenv("B200_DISABLE_CAM_MAJOR") == nullptr) {
+  if (!has_dups && dev_env("B200_DISABLE_CAM_MAJOR") == nullptr) {
     h->num_cam_items = static_cast<int>(cam_items.size());
     OK(dev_alloc(&h->d_cam_items, cam_items.size()));
     OK(dev_alloc(&h->d_cam_rows, n));
@@ -1643,7 +1476,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     h->v2.per_warp_bytes = v2_per_warp_bytes(v2_stages, kV2Scratch);
     h->v2_smem = v2_sy_bytes(max_cam_span, v2_replicas) + static_cast<size_t>(v2_warps) * h->v2.per_warp_bytes;
     h->v2_mul = h->v2;
-    if (mul_warps > 0 && getenv("B200_MUL_V2") == nullptr) {
+    {
       h->v2_mul.warps = mul_warps;
       h->v2_mul.stages = mul_stages;
       h->v2_mul.replicas = mul_replicas;
@@ -1653,25 +1486,23 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       // the S*x kernel takes the >32-row points itself when its TMA rings can stage a kTile-row point
       h->big_folded = mul_warps >= kTile / 32 &&
                       static_cast<size_t>(mul_warps) * h->v2_mul.per_warp_bytes >= kTile * 192 + 160 &&
-                      getenv("B200_DISABLE_BIG_FOLD") == nullptr;
+                      dev_env("B200_DISABLE_BIG_FOLD") == nullptr;
       CU(cudaFuncSetAttribute(schur_mul_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-    } else {
-      h->mul_smem = h->v2_smem;
     }
     // v4 (all operands through the TMA ring, x staged in shared memory): needs the narrow camera ranges of the
     // direct-flush mode; up to 16 warps with a one-slot ring each, one private camera vector per warp when they fit.
-    if (h->mul_v3 && h->v2.direct && getenv("B200_MUL_V3") == nullptr) {
+    if (h->mul_v3 && h->v2.direct && dev_env("B200_MUL_V3") == nullptr) {
       const long total = static_cast<long>(prop.sharedMemPerBlockOptin) - 2048;
       const long sy1 = static_cast<long>(v2_sy_bytes(max_cam_span, 1));
       int w4 = kV4MaxThreads / 32;
-      if (const char* e = getenv("B200_V4_WARPS")) w4 = std::max(4, std::min(w4, atoi(e)));
+      if (const char* e = dev_env("B200_V4_WARPS")) w4 = std::max(4, std::min(w4, atoi(e)));
       int st4 = 1;  // the slot is refilled as soon as its contents are in registers: one stage per warp, more warps
-      if (const char* e = getenv("B200_V4_STAGES")) st4 = std::max(1, std::min(3, atoi(e)));
+      if (const char* e = dev_env("B200_V4_STAGES")) st4 = std::max(1, std::min(3, atoi(e)));
       for (; w4 >= 8; --w4) {
         const long rem = total - static_cast<long>(w4) * v4_per_warp_bytes(st4) - sy1 /* staged x */;
         if (rem < sy1) continue;
         int rep4 = static_cast<int>(std::min<long>(w4, rem / sy1));
-        if (const char* e = getenv("B200_V4_REPLICAS")) rep4 = std::max(1, std::min(rep4, atoi(e)));
+        if (const char* e = dev_env("B200_V4_REPLICAS")) rep4 = std::max(1, std::min(rep4, atoi(e)));
         std::vector<uint32_t> meta(static_cast<size_t>(wtiles.size()) * kV4MetaWords, 0u);
         for (int b = 0; b < num_ctas_v2; ++b)
           for (int t = cta_part[b].x; t < cta_part[b].y; ++t) {
@@ -1699,19 +1530,16 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->v2_mul.stage_x = 1;
         h->mul_smem = v2_sy_bytes(max_cam_span, rep4) + v4_sx_bytes(max_cam_span, 1) + static_cast<size_t>(w4) * h->v2_mul.per_warp_bytes;
         h->mul_v4 = true;
-        h->big_folded = getenv("B200_DISABLE_BIG_FOLD") == nullptr;
+        h->big_folded = dev_env("B200_DISABLE_BIG_FOLD") == nullptr;
         h->mul_v4_owned = rep4 == w4;
         CU(cudaFuncSetAttribute(jtj_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(jtj_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-        CU(cudaFuncSetAttribute(pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-        CU(cudaFuncSetAttribute(pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(schur_mul_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         break;
       }
     }
     // function attributes are process-wide: always raise them to the device limit, never to this handle's need
-    CU(cudaFuncSetAttribute(schur_mul_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     CU(cudaFuncSetAttribute(jtj_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
     if (!h->big_folded) {
       // the S*x kernel must not take the >32-row points itself when they are handled by a separate launch
@@ -1722,63 +1550,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       h->v2_mul.cta_big = none;
     }
     h->v2_ok = true;
-    // Opt-in experiment (B200_SPLIT_PCG=1): split-phase PCG without any grid-wide barrier (pcg_split.cuh).  Measured
-    // within +-1.5 % of the default on the large problems and 13 % slower on C16 (the tests move into the product's
-    // prologue): the iteration is bound by its two kernel boundaries, not by the grid sync of the vector kernel.
-    if (h->mul_v4 && h->world == 1 && h->big_folded && h->v2.direct && h->num_huge == 0 && getenv("B200_SPLIT_PCG") != nullptr) {
-      // camera ownership for the D_f^2 p^2 term of p.q: the first CTA whose range contains the camera; every camera
-      // must be covered by the (sorted) ranges
-      std::vector<int2> own(num_ctas_v2, make_int2(0, 0));
-      int covered = 0;
-      bool gapless = true;
-      for (int b = 0; b < num_ctas_v2; ++b) {
-        if (cta_cam[b].y <= cta_cam[b].x) continue;
-        if (cta_cam[b].x > covered) gapless = false;
-        const int lo = std::max(cta_cam[b].x, covered);
-        if (lo < cta_cam[b].y) {
-          own[b] = make_int2(lo, cta_cam[b].y);
-          covered = cta_cam[b].y;
-        }
-      }
-      if (gapless && covered == C) {
-        OK(dev_alloc(&h->d_cta_own, own.size()));
-        CU(cudaMemcpyAsync(h->d_cta_own, own.data(), own.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-        h->split_grid = (C + kSplitCamsPerCta - 1) / kSplitCamsPerCta;
-        OK(dev_alloc(&h->d_split_red, static_cast<size_t>(h->split_grid) * 4));
-        OK(dev_alloc(&h->d_cg3, 3));
-        CU(cudaMemsetAsync(h->d_cg3, 0, 3 * sizeof(CgState), h->stream));
-        if (h->d_qa == nullptr) {
-          OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
-          OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
-        }
-        CU(cudaFuncSetAttribute(schur_mul_v4_pcg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-        CU(cudaFuncSetAttribute(schur_mul_v4_pcg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-        CU(cudaStreamSynchronize(h->stream));
-        h->split_ok = true;
-      }
-    }
-    // Opt-in experiment (B200_PCG_PERSISTENT=1): the whole PCG as one persistent kernel.  Measured SLOWER than one
-    // product launch + one vector launch per iteration (59 vs 43 us per iteration on Ladybug-1723: software grid
-    // barriers and the serial vector phases on 148 fat CTAs cost more than two kernel boundaries; see
-    // profiles/r01_pcg_persistent_trace_l1723.txt), so the multi-kernel PCG stays the default.
-    if (h->mul_v4 && h->world == 1 && h->big_folded && h->num_huge == 0 && getenv("B200_PCG_PERSISTENT") != nullptr) {
-      const int cpc = (C + num_ctas_v2 - 1) / num_ctas_v2;
-      int per_sm = 0;
-      if (h->mul_v4_owned) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<true>, 32 * h->v2_mul.warps, h->mul_smem));
-      else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_kernel<false>, 32 * h->v2_mul.warps, h->mul_smem));
-      if (9 * cpc <= 32 * h->v2_mul.warps && per_sm >= 1 && prop.cooperativeLaunch) {
-        if (h->d_qa == nullptr) {
-          OK(dev_alloc(&h->d_qa, 9 * static_cast<size_t>(C)));
-          OK(dev_alloc(&h->d_qb, 9 * static_cast<size_t>(C)));
-        }
-        OK(dev_alloc(&h->d_pcg_red, static_cast<size_t>(num_ctas_v2) * 8));
-        OK(dev_alloc(&h->d_pcg_barrier, 4));
-        CU(cudaMemsetAsync(h->d_pcg_red, 0, sizeof(double) * num_ctas_v2 * 8, h->stream));
-        h->pcg_cams_per_cta = cpc;
-        h->pcg_ok = true;
-      }
-    }
-    if (h->v2.direct && getenv("B200_DISABLE_V2B") == nullptr) {
+    if (h->v2.direct && dev_env("B200_DISABLE_V2B") == nullptr) {
       const size_t lim = prop.sharedMemPerBlockOptin - 2048;
       // Each kernel gets as many replicas of its private accumulators as fit next to its per-warp buffers
       // (one per warp at best), and a shallower TMA ring if even a single replica would not fit.
@@ -1821,10 +1593,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
 
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
-            "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d pcg=%d split=%d\n",
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
             C, P, N, wtiles.size(), big_tiles.size(), h->num_huge, max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
             h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
-            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->pcg_ok ? 1 : 0, h->split_ok ? 1 : 0);
+            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -1843,20 +1615,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     const int nblocks = (C + kCgCamsPerCta - 1) / kCgCamsPerCta;
     h->cg_grid = std::max(1, std::min(nblocks, per_sm * h->sm_count));
     OK(dev_alloc(&h->d_red, static_cast<size_t>(h->cg_grid) * 4));
-    OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(std::max(h->cg_grid, kCgClusterSize))));
-    {
-      const int cpc = (C + kCgClusterSize - 1) / kCgClusterSize;
-      const size_t need = sizeof(double) * 9 * static_cast<size_t>(cpc);
-      // Opt-in experiment (B200_CG_CLUSTER=1): measured slower than the 62-CTA cooperative kernel (18 vs 12 us per
-      // launch on Ladybug-1723 -- eight SMs serialise the L2 round trips that 62 SMs overlap).
-      if (need + 8192 <= prop.sharedMemPerBlockOptin && getenv("B200_CG_CLUSTER") != nullptr) {
-        // (function attributes are process-wide: raise to the device limit, never to this handle's need)
-        CU(cudaFuncSetAttribute(cg_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 4096));
-        h->cg_cluster_cams = cpc;
-      }
-    }
+    OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(h->cg_grid)));
     OK(dev_alloc(&h->d_pq_parts, static_cast<size_t>(prop.multiProcessorCount)));
-    CU(cudaMemsetAsync(h->d_seed_pq, 0, sizeof(double) * std::max(h->cg_grid, kCgClusterSize), h->stream));
+    CU(cudaMemsetAsync(h->d_seed_pq, 0, sizeof(double) * h->cg_grid, h->stream));
     CU(cudaMemsetAsync(h->d_pq_parts, 0, sizeof(double) * prop.multiProcessorCount, h->stream));
   }
 
@@ -1890,7 +1651,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_qa, h->d_qb, h->d_pcg_red, h->d_pcg_barrier, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_cta_own, h->d_cg3, h->d_split_red, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
@@ -2012,7 +1773,7 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
   const size_t off = 3 * static_cast<size_t>(h->P);
   const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
   const int nc = 9 * h->C;
-  if (h->mul_v4 && h->v2.direct && getenv("B200_NO_JTJ_V4") == nullptr) {
+  if (h->mul_v4 && h->v2.direct && dev_env("B200_NO_JTJ_V4") == nullptr) {
     // v4 machinery (jtj_v4_kernel): seed y = D^2 x everywhere, the tile kernel adds J'(J x)
     OK(launch(h, K_MISC, [&] {
       diag_sq_mul_kernel<<<flat_grid(h, off, 256), 256, 0, h->stream>>>(static_cast<int>(off), dD, h->d_vp0, h->d_vp1, nullptr);

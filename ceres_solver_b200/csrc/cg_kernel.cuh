@@ -387,284 +387,4 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// The same vector update as cg_vector_kernel, as ONE thread-block cluster of 8 CTAs x 1024 threads: the two
-// grid-wide reductions become cluster-wide ones (partials in each CTA's shared memory, read by every CTA through
-// DSMEM after a hardware cluster barrier), which costs a fraction of a cooperative grid sync.  The camera-sized
-// vectors of a bundle-adjustment problem (1.5e4 .. 1.2e5 entries) are one or a few entries per thread, so eight SMs are
-// plenty in principle -- but measured SLOWER than the cooperative kernel (18 vs 12 us per launch on Ladybug-1723: the
-// dependent L2 round trips of the phases are spread over 8 SMs instead of 62), so it is an opt-in experiment
-// (B200_CG_CLUSTER=1).  CTAs own contiguous camera ranges; r of the range is staged in shared memory for the 9x9
-// block-diagonal preconditioner.
-// ------------------------------------------------------------------------------------------------
-constexpr int kCgClusterSize = 8;
-constexpr int kCgClusterThreads = 1024;
-
-__device__ __forceinline__ void cgc_block_sum3(double& a, double& b, double& c, double (*scratch)[3]) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-    c += __shfl_xor_sync(0xffffffffu, c, o);
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) {
-    scratch[warp][0] = a;
-    scratch[warp][1] = b;
-    scratch[warp][2] = c;
-  }
-  __syncthreads();
-  a = b = c = 0.0;
-#pragma unroll
-  for (int w = 0; w < kCgClusterThreads / 32; ++w) {
-    a += scratch[w][0];
-    b += scratch[w][1];
-    c += scratch[w][2];
-  }
-}
-
-__global__ void __cluster_dims__(kCgClusterSize, 1, 1) __launch_bounds__(kCgClusterThreads, 1)
-    cg_cluster_kernel(CgVecArgs a, int cams_per_cta) {
-  cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ __align__(16) double s_r[];           // [9 * cams_per_cta]
-  __shared__ double scratch[kCgClusterThreads / 32][3];
-  __shared__ double s_part[4];                             // this CTA's partial sums, read by the whole cluster
-  __shared__ double s_tot[4];
-  CgState* st = a.st;
-  const int mode = a.mode;
-  if (mode != CG_BEGIN && st->done) return;  // every CTA takes this branch together
-  const double rho_old = (mode == CG_BEGIN) ? 1.0 : st->rho;
-  const double Q0 = st->Q0, tol_r = st->tol_r;
-  const int it = (mode == CG_BEGIN) ? 0 : st->iteration + (mode == CG_RESET_SECOND ? 0 : 1);
-  const int tid = threadIdx.x;
-  const int rank = static_cast<int>(cluster.block_rank());
-  const int cam0 = rank * cams_per_cta;
-  const int n_own = 9 * max(0, min(cams_per_cta, a.C - cam0));
-  const int j0 = 9 * cam0;
-  const bool writer = (rank == 0 && tid == 0);
-  const bool fused_pq = a.pq_parts != nullptr;
-
-  // cluster-wide fixed-order totals of s_part[slot0 .. slot0 + count)
-  auto cluster_totals = [&](int slot0, int count, double* out) {
-    cluster.sync();
-    if (tid < count) {
-      double acc = 0.0;
-      for (int r = 0; r < kCgClusterSize; ++r) acc += *cluster.map_shared_rank(&s_part[slot0 + tid], r);
-      s_tot[slot0 + tid] = acc;
-    }
-    __syncthreads();
-    for (int k = 0; k < count; ++k) out[k] = s_tot[slot0 + k];
-  };
-
-  // ------------------------------------------------------------------ p.q
-  double alpha = 0.0;
-  if (mode == CG_NORMAL || mode == CG_RESET_FIRST) {
-    double pq;
-    if (fused_pq) {
-      const int warp = tid >> 5, lane = tid & 31;
-      if (warp < 2) {
-        double acc = 0.0;
-        if (warp == 0) {
-          for (int b = lane; b < a.num_pq_parts; b += 32) acc += __ldcg(a.pq_parts + b);
-        } else {
-          for (int b = lane; b < kCgClusterSize; b += 32) acc += __ldcg(a.seed_pq + b);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) s_tot[warp] = acc;
-      }
-      __syncthreads();
-      pq = s_tot[0] + s_tot[1];
-      __syncthreads();
-    } else {
-      double acc = 0.0, d1 = 0.0, d2 = 0.0;
-      for (int e = tid; e < n_own; e += kCgClusterThreads) acc += a.p[j0 + e] * a.q[j0 + e];
-      cgc_block_sum3(acc, d1, d2, scratch);
-      if (tid == 0) s_part[0] = acc;
-      cluster_totals(0, 1, &pq);
-    }
-    bool stop = false;
-    int term = 0, reason = 0;
-    if (!(pq > 0.0) || isinf(pq)) {
-      stop = true;
-      term = isnan(pq) ? 2 : 1;
-      reason = 6;
-    } else {
-      alpha = rho_old / pq;
-      if (isinf(alpha)) {
-        stop = true;
-        term = 2;
-        reason = 7;
-      }
-    }
-    if (stop) {
-      if (writer) {
-        st->pq = pq;
-        st->done = 1;
-        st->termination = term;
-        st->reason = reason;
-        st->iteration = it;
-      }
-      cluster.sync();  // nobody leaves while its shared memory may still be read
-      return;
-    }
-  }
-
-  // ------------------------------------------------------------------ x, r, z = M^-1 r, partial sums
-  double accQ = 0.0, accR = 0.0, accRho = 0.0;
-  for (int e = tid; e < n_own; e += kCgClusterThreads) {
-    const int j = j0 + e;
-    const double bj = a.rhs[j];
-    const double dj = a.Df != nullptr ? a.Df[j] : 0.0;
-    double xj = 0.0, rj;
-    if (mode == CG_BEGIN) {
-      rj = bj;
-      a.x[j] = 0.0;
-    } else if (mode == CG_RESET_SECOND) {
-      xj = a.x[j];
-      rj = bj - a.q[j];                     // r = b - S x   (q holds S x here)
-    } else {
-      const double pj = a.p[j];
-      xj = a.x[j] + alpha * pj;
-      a.x[j] = xj;
-      rj = a.r[j] - alpha * a.q[j];
-      if (mode == CG_RESET_FIRST && a.seed_target != nullptr) a.seed_target[j] = dj * dj * xj;
-    }
-    if (mode != CG_RESET_FIRST) {
-      a.r[j] = rj;
-      s_r[e] = rj;
-      accQ += xj * (bj + rj);
-      accR += rj * rj;
-    }
-  }
-  if (mode == CG_RESET_FIRST) {
-    if (writer) {
-      st->alpha = alpha;
-      st->iteration = it;   // iteration `it` is half done; the second half reads it back
-    }
-    cluster.sync();
-    return;
-  }
-  __syncthreads();
-  for (int e = tid; e < n_own; e += kCgClusterThreads) {
-    const int j = j0 + e;
-    double zj;
-    if (a.precond == 0) {
-      zj = s_r[e];
-    } else {
-      const int cl = e / 9;
-      const double* m = a.minv + 9 * static_cast<size_t>(j);   // row (j % 9) of block (j / 9)
-      const double* rc = s_r + 9 * cl;
-      zj = 0.0;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) zj += m[k] * rc[k];
-    }
-    a.z[j] = zj;
-    accRho += s_r[e] * zj;
-  }
-  cgc_block_sum3(accQ, accR, accRho, scratch);
-  if (tid == 0) {
-    s_part[1] = accQ;
-    s_part[2] = accR;
-    s_part[3] = accRho;
-  }
-  double tot[3];
-  cluster_totals(1, 3, tot);
-
-  // ------------------------------------------------------------------ tests, beta, p
-  const double dotQ = tot[0], sqR = tot[1], rho_new = tot[2];
-  const double norm_r = sqrt(sqR);
-  double Q0_next = 0.0;
-  bool leave = false;
-  if (mode == CG_BEGIN) {
-    if (writer) {
-      st->norm_rhs = norm_r;
-      st->tol_r = a.prm.r_tolerance * norm_r;
-      st->norm_r = norm_r;
-      st->Q0 = 0.0;
-      st->iteration = 0;
-      st->done = 0;
-      st->termination = 1;
-      st->reason = 0;
-      st->last_rho = 1.0;
-    }
-    const double tol0 = a.prm.r_tolerance * norm_r;
-    if (norm_r == 0.0 || (a.prm.min_iterations == 0 && norm_r <= tol0)) {
-      if (writer) {
-        st->done = 1;
-        st->termination = 0;
-        st->reason = norm_r == 0.0 ? 8 : 2;
-      }
-      leave = true;
-    }
-  } else {
-    const double Q1 = -dotQ;
-    const double zeta = it * (Q1 - Q0) / Q1;
-    int done = 0, term = 1, reason = 0;
-    if (zeta < a.prm.q_tolerance && it >= a.prm.min_iterations) {
-      done = 1; term = 0; reason = 1;
-    } else if (norm_r <= tol_r && it >= a.prm.min_iterations) {
-      done = 1; term = 0; reason = 2;
-    } else if (it >= a.prm.max_iterations) {
-      done = 1; term = 1; reason = 3;
-    }
-    if (done) {
-      if (writer) {
-        st->norm_r = norm_r;
-        st->iteration = it;
-        st->done = 1;
-        st->termination = term;
-        st->reason = reason;
-      }
-      leave = true;
-    }
-    Q0_next = Q1;
-  }
-  double beta = 0.0;
-  if (!leave) {
-    int fail_reason = 0;
-    if (zero_or_inf(rho_new) || isnan(rho_new)) {
-      fail_reason = 4;
-    } else if (it >= 1) {
-      beta = rho_new / rho_old;
-      if (zero_or_inf(beta)) fail_reason = 5;
-    }
-    if (fail_reason) {
-      if (writer) {
-        st->iteration = it + 1;
-        st->done = 1;
-        st->termination = 2;
-        st->reason = fail_reason;
-      }
-      leave = true;
-    }
-  }
-  if (!leave) {
-    double seed_acc = 0.0, d1 = 0.0, d2 = 0.0;
-    for (int e = tid; e < n_own; e += kCgClusterThreads) {
-      const int j = j0 + e;
-      const double zj = a.z[j];   // own store, same thread
-      const double pn = (it == 0) ? zj : zj + beta * a.p[j];
-      a.p[j] = pn;
-      const double d = a.Df != nullptr ? a.Df[j] : 0.0;
-      if (a.seed_target != nullptr) a.seed_target[j] = d * d * pn;
-      seed_acc += d * d * pn * pn;
-    }
-    if (a.seed_pq != nullptr) {
-      cgc_block_sum3(seed_acc, d1, d2, scratch);
-      if (tid == 0) a.seed_pq[rank] = seed_acc;
-    }
-    if (writer) {
-      st->norm_r = norm_r;
-      st->last_rho = rho_old;
-      st->rho = rho_new;
-      st->Q0 = Q0_next;
-      st->iteration = it;
-    }
-  }
-  cluster.sync();  // nobody leaves while its partials may still be read through DSMEM
-}
-
-
 }  // namespace b200

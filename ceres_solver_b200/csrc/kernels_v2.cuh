@@ -169,146 +169,12 @@ __device__ __forceinline__ void cam_accumulate9(double* sy_rep, int cam_local, b
   }
 }
 
-// Row data of one warp tile that does not come through the TMA ring; loaded one tile ahead.
-struct RowPre {
-  WarpTile wt;
-  uint32_t meta;
-  double2 e0, e1, e2;
-};
-
-__device__ __forceinline__ void v2_load_row(const V2View& v, int tile, int tile_end, RowPre& r) {
-  const int lane = threadIdx.x & 31;
-  if (tile < tile_end) {
-    r.wt = v.wtiles[tile];
-    if (lane < r.wt.row_count) {
-      const size_t row = static_cast<size_t>(r.wt.row_begin) + lane;
-      r.meta = __ldg(v.row_meta + row);
-      const double2* ep = reinterpret_cast<const double2*>(v.p.E() + 6 * row);
-      r.e0 = __ldg(ep);
-      r.e1 = __ldg(ep + 1);
-      r.e2 = __ldg(ep + 2);
-    } else {
-      r.meta = 0u;
-      r.e0 = r.e1 = r.e2 = make_double2(0.0, 0.0);
-    }
-  } else {
-    r.wt.row_begin = 0;
-    r.wt.pt_begin = 0;
-    r.wt.row_count = 0;
-    r.wt.pt_count = 0;
-    r.meta = 0u;
-    r.e0 = r.e1 = r.e2 = make_double2(0.0, 0.0);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// partial_y(camera part) = F'(F x - E (E'E+D^2)^-1 E'F x)     x: [9C]
-// Software pipeline per warp: the F cells of tile i+1.. are in flight in the TMA ring, the E cells / row meta of
-// tile i+1 are loaded before tile i's arithmetic, and the x / (E'E)^-1 gathers of tile i+1 are issued before
-// tile i's shared-memory accumulation, so every global latency overlaps work of the previous tile.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kV2MaxThreads, 1)
-    schur_mul_v2_kernel(V2View v, const double* __restrict__ ete_inv, const double* __restrict__ x, double* y,
-                        const int* __restrict__ done_flag) {
-  if (done_flag != nullptr && *done_flag != 0) return;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* sy = reinterpret_cast<double*>(smem_raw);
-  const WarpCtx c = v2_warp_ctx(v, smem_raw, kV2Scratch);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int2 part = v.cta_part[blockIdx.x];
-  const int2 cr = v.cta_cam[blockIdx.x];
-  int t_issue;
-  v2_prologue(v, sy, c, part, cr, t_issue);
-
-  RowPre cur, nxt;
-  double xc[9], pinv[6], xn[9], pn[6];
-  v2_load_row(v, part.x + warp, part.y, cur);
-  bool active = lane < cur.wt.row_count;
-  int cam = static_cast<int>(cur.meta & 0x7fffffffu);
-  Seg sg = v2_segment(active && (cur.meta >> 31), cur.wt.row_count);
-  if (active) {
-    const double* xcp = x + 9 * static_cast<size_t>(cam);
-#pragma unroll
-    for (int k = 0; k < 9; ++k) xc[k] = __ldg(xcp + k);
-    const double* pi = ete_inv + 6 * static_cast<size_t>(cur.wt.pt_begin + sg.lpt);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) pinv[k] = __ldg(pi + k);
-  }
-  int it = 0;
-  for (int tile = part.x + warp; tile < part.y; tile += v.warps, ++it) {
-    const int s = it % v.stages;
-    const uint32_t parity = (it / v.stages) & 1;
-    v2_load_row(v, tile + v.warps, part.y, nxt);  // E cells + meta of the next tile: in flight during this tile
-    mbar_wait(c.bars + s, parity);
-    double f[18];
-    double t0 = 0.0, t1 = 0.0;
-    if (active) {
-      const double* fr = c.sF + s * 576 + lane * 18;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double2 a = lds2(fr + 2 * k);
-        f[2 * k] = a.x;
-        f[2 * k + 1] = a.y;
-      }
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        t0 += f[k] * xc[k];
-        t1 += f[9 + k] * xc[k];
-      }
-      c.sW[lane * 3 + 0] = cur.e0.x * t0 + cur.e1.y * t1;
-      c.sW[lane * 3 + 1] = cur.e0.y * t0 + cur.e2.x * t1;
-      c.sW[lane * 3 + 2] = cur.e1.x * t0 + cur.e2.y * t1;
-    }
-    __syncwarp();
-    double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (active) {
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-      for (int j = sg.first; j < sg.end; ++j) {
-        u0 += c.sW[j * 3 + 0];
-        u1 += c.sW[j * 3 + 1];
-        u2 += c.sW[j * 3 + 2];
-      }
-      const double v0 = -(pinv[0] * u0 + pinv[1] * u1 + pinv[2] * u2);
-      const double v1 = -(pinv[1] * u0 + pinv[3] * u1 + pinv[4] * u2);
-      const double v2 = -(pinv[2] * u0 + pinv[4] * u1 + pinv[5] * u2);
-      t0 += cur.e0.x * v0 + cur.e0.y * v1 + cur.e1.x * v2;
-      t1 += cur.e1.y * v0 + cur.e2.x * v1 + cur.e2.y * v2;
-#pragma unroll
-      for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
-    }
-    // gathers for the next tile (depend on its meta, which was requested before this tile's arithmetic)
-    const bool nactive = lane < nxt.wt.row_count;
-    const int ncam = static_cast<int>(nxt.meta & 0x7fffffffu);
-    const Seg nsg = v2_segment(nactive && (nxt.meta >> 31), nxt.wt.row_count);
-    if (nactive) {
-      const double* xcp = x + 9 * static_cast<size_t>(ncam);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) xn[k] = __ldg(xcp + k);
-      const double* pi = ete_inv + 6 * static_cast<size_t>(nxt.wt.pt_begin + nsg.lpt);
-#pragma unroll
-      for (int k = 0; k < 6; ++k) pn[k] = __ldg(pi + k);
-    }
-    cam_accumulate9(sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span), cam - cr.x, active, g);
-    __syncwarp();
-    if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
-    t_issue += v.warps;
-    cur = nxt;
-    active = nactive;
-    cam = ncam;
-    sg = nsg;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) xc[k] = xn[k];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) pinv[k] = pn[k];
-  }
-  v2_epilogue(v, sy, cr, y);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Same product, tuned for occupancy instead of per-warp latency: nothing is carried in registers from one tile to the
-// next (the E cells, row words and (E'E)^-1 of the NEXT tile are only pulled towards L2 with prefetch.global.L2, one
-// 128-byte line per lane), which brings the kernel under 128 registers so that 16 warps per SM are resident
-// (ncu on the register-pipelined variant: 162 registers -> 12 warps, issue slots 32 % busy, 47 us on Ladybug-1723).
+// partial_y(camera part) = F'(F x - E (E'E+D^2)^-1 E'F x)     x: [9C]   -- the product for problems WITHOUT camera
+// locality (every CTA touches cameras all over the index range: per-CTA partial vectors + cam_reduce_kernel).
+// F cells through the per-warp TMA ring; nothing is carried in registers from one tile to the next (the E cells, row
+// words and (E'E)^-1 of the NEXT tile are only pulled towards L2 with prefetch.global.L2, one 128-byte line per lane),
+// which keeps the kernel under 128 registers so that 16 warps per SM are resident.
 // ------------------------------------------------------------------------------------------------
 // The few points with 33..kTile rows that fall inside this CTA's row range: processed by the whole CTA after the
 // warp tiles (the warps' TMA rings are idle by then and provide the staging memory), one point at a time:

