@@ -28,8 +28,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_TRAFFIC = {("ladybug-1723", "schur_multiply"): 141.92e6 + 4.14e6, ("venice-1778", "schur_multiply"): 1036.3e6 + 4.2e6}
+
+
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel on this workload, from the committed
+    `ncu --set full` captures (profiles/ncu_traffic.json, written by tools/ncu_summary.py); None if never captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload, {}).get(kernel)
+    except Exception:
+        return None
+
+
+def op_rate(v, peak):
+    """GB/s of an operation class: bytes of ONE operation x operations / event time of ALL its launches."""
+    if not v or v.get("ms", 0) <= 0 or v.get("operations", 0) <= 0 or v.get("bytes_per_operation", 0) <= 0:
+        return None
+    gbps = v["bytes_per_operation"] * v["operations"] / (v["ms"] * 1e-3) / 1e9
+    return {"GBps": round(gbps, 1), "frac": round(gbps / peak, 4), "operations": v["operations"],
+            "launches": v["launches"], "mean_op_ms": round(v["ms"] / v["operations"], 5),
+            "bytes_per_operation": v["bytes_per_operation"]}
 
 METRIC = "lm_iterations_per_sec"
 UNIT = "LM iterations/s"
@@ -106,6 +124,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def make_config(desc, num_obs):
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    jb = 192 * num_obs
+    return {"workload": desc, "linear_solver": "ITERATIVE_SCHUR", "preconditioner": "SCHUR_JACOBI", "eta": 1e-2,
+            "max_linear_solver_iterations": 500, "jacobian_bytes": jb,
+            "l2": "inputs larger than L2 (J alone is %.0f MB)" % (jb / 1e6) if jb > 126e6
+            else "working set fits L2: roofline fraction is vs HBM peak and may exceed 1"}
+
+
 def run_reference(args, bal, desc, rank0=True):
     """The reference's own CPU path (restated in oracle/: the real Ceres cannot be built in this image — Eigen is
     absent) on all host threads, same problem, same options."""
@@ -153,8 +180,10 @@ def main():
                 "steps": r["iterations"], "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["iterations"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic" if workload != "c16" else "real BAL file shipped with the reference",
-                "config": {"workload": desc, "linear_solver": "ITERATIVE_SCHUR", "preconditioner": "SCHUR_JACOBI",
-                           "eta": 1e-2, "max_linear_solver_iterations": 500},
+                "config": make_config(desc, bal.N),
+                "cg_iterations": [int(t["ls_iterations"]) for t in r["trace"][1:]],
+                "costs": [float(t["cost"]) for t in r["trace"]], "final_cost": float(r["trace"][-1]["cost"]),
+                "step_norms": [float(t["step_norm"]) for t in r["trace"]],
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                  "sample": "%d LM iterations from the initial point, %d CG iterations" % (
                                      r["iterations"], sum(int(t["ls_iterations"]) for t in r["trace"]))},
@@ -254,10 +283,7 @@ def main():
             for _ in range(5):
                 gpu.jtj_multiply(xj, Dj)
             sj = gpu.stats().get("jtj_multiply")
-            if sj and sj["ms"] > 0 and sj["launches"] > 0:
-                gbps = sj["bytes_per_launch"] * sj["launches"] / (sj["ms"] * 1e-3) / 1e9
-                jtj = {"GBps": round(gbps, 1), "frac": round(gbps / peak, 4), "launches": sj["launches"],
-                       "mean_launch_ms": round(sj["ms"] / sj["launches"], 4), "bytes_per_launch": sj["bytes_per_launch"]}
+            jtj = op_rate(sj, peak)
         except Exception as e:  # never let the extra measurement take the bench line down
             jtj = {"error": str(e)[:200]}
         finally:
@@ -266,48 +292,61 @@ def main():
             except Exception:
                 pass
     total_ms = sum(v["ms"] for v in stats.values())
-    by_time = max(((k, v) for k, v in stats.items() if v["bytes_per_launch"] > 0), key=lambda kv: kv[1]["ms"])[0]
+    # S*x: the product's own launch plus, where a problem needs them, the >32-row-point launch and the fixed-order
+    # reduction of per-CTA partials -- all billed to the one operation
+    sx = dict(stats.get("schur_multiply", {"ms": 0.0, "operations": 0, "launches": 0, "bytes_per_operation": 0.0}))
+    for extra in ("schur_multiply_big_points", "camera_reduce"):
+        if extra in stats:
+            sx["ms"] += stats[extra]["ms"]
+            sx["launches"] += stats[extra]["launches"]
+    rates = {k: op_rate(v, peak) for k, v in stats.items() if v["operations"] > 0 and v["bytes_per_operation"] > 0}
+    rates["schur_multiply"] = op_rate(sx, peak)
+    by_time = max(((k, v) for k, v in stats.items() if v["bytes_per_operation"] > 0), key=lambda kv: kv[1]["ms"])[0]
     # the roofline line is about the kernel north_star names (the implicit-Schur product feeding CG), which is also
     # the dominant kernel on the default workload; `dominant_kernel_by_time` says which HBM kernel took most time here
-    dom_name = "schur_multiply" if stats.get("schur_multiply", {}).get("launches", 0) > 0 else by_time
-    dom = stats[dom_name]
-    achieved = dom["bytes_per_launch"] * dom["launches"] / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
-    kernels = {k: {"launches": v["launches"], "ms": round(v["ms"], 4),
+    dom_name = "schur_multiply" if sx["operations"] > 0 else by_time
+    dom = rates[dom_name]
+    kernels = {k: {"launches": v["launches"], "operations": v["operations"], "ms": round(v["ms"], 4),
                    "share": round(v["ms"] / total_ms, 4) if total_ms > 0 else 0.0,
-                   "GBps": round(v["bytes_per_launch"] * v["launches"] / (v["ms"] * 1e-3) / 1e9, 1)
-                   if v["ms"] > 0 and v["bytes_per_launch"] > 0 else None}
+                   "GBps": rates[k]["GBps"] if k in rates and rates[k] else None}
                for k, v in stats.items() if v["launches"] > 0}
 
-    # "Schur-eliminate" of the metric = (E'E + D^2)^-1, reduced rhs and the block diagonal of S (SCHUR_JACOBI)
+    # "Schur-eliminate" of the metric = (E'E + D^2)^-1, reduced rhs and the block diagonal of S (SCHUR_JACOBI):
+    # two passes over J here (point-major, then camera-major); `frac` bills each pass its own algorithmic bytes,
+    # `frac_single_pass` bills the whole elimination SURVEY 8d's one-pass figure (216 N + vectors)
     elim = None
-    parts = [stats[k] for k in ("schur_init", "schur_diag_blocks") if stats.get(k, {}).get("launches", 0) > 0 and stats[k]["ms"] > 0]
-    if parts:
-        eb = sum(v["bytes_per_launch"] * v["launches"] for v in parts)
+    parts = [stats[k] for k in ("schur_init", "schur_diag_blocks") if stats.get(k, {}).get("operations", 0) > 0 and stats[k]["ms"] > 0]
+    if len(parts) == 2:
+        n_ops = min(v["operations"] for v in parts)
+        eb = sum(v["bytes_per_operation"] * v["operations"] for v in parts)
         et = sum(v["ms"] for v in parts) * 1e-3
-        elim = {"GBps": round(eb / et / 1e9, 1), "frac": round(eb / et / 1e9 / peak, 4)}
+        one_pass = (216.0 * rp.N + 8.0 * (3 * rp.P + 9 * rp.C) + 720.0 * rp.C) * n_ops
+        elim = {"GBps": round(eb / et / 1e9, 1), "frac": round(eb / et / 1e9 / peak, 4), "operations": n_ops,
+                "mean_op_ms": round(1e3 * et / n_ops, 4), "frac_single_pass": round(one_pass / et / 1e9 / peak, 4)}
     line = {"metric": METRIC, "value": iters / dev_s, "unit": UNIT, "n_gpus": world, "steps": iters,
             "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / iters, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64",
             "data": "synthetic" if workload != "c16" else "real BAL file shipped with the reference",
-            "config": {"workload": desc, "linear_solver": "ITERATIVE_SCHUR", "preconditioner": "SCHUR_JACOBI",
-                       "eta": 1e-2, "max_linear_solver_iterations": 500, "jacobian_bytes": 192 * rp.N,
-                       "l2": "inputs larger than L2 (J alone is %.0f MB)" % (192 * rp.N / 1e6)
-                       if 192 * rp.N > 126e6 else "working set fits L2: roofline fraction is vs HBM peak and may exceed 1",
-                       "cg_iterations": [r["ls_iterations"] for r in recs[1:]]},
+            "config": make_config(desc, rp.N),
+            "cg_iterations": [r["ls_iterations"] for r in recs[1:]],
+            "costs": [r["cost"] for r in recs], "step_norms": [r["step_norm"] for r in recs],
             "e2e": {"value": e2e_iters / e2e_wall_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_iters,
                     "d2h_bytes_per_step": d2h // e2e_iters, "device_seconds": e2e_dev_s, "wall_seconds": e2e_wall_s},
             "gpu_launches": launches, "clocks": clocks, "wall_seconds": wall_s,
-            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get((workload, dom_name)), "peak_source": peak_src,
-                         "bytes_per_launch": dom["bytes_per_launch"], "launches": dom["launches"],
-                         "dominant_kernel_by_time": by_time,
-                         "mean_launch_ms": dom["ms"] / max(1, dom["launches"])},
+            "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": dom["frac"], "traffic": ncu_traffic(workload, dom_name), "peak_source": peak_src,
+                         "bytes_per_operation": dom["bytes_per_operation"], "operations": dom["operations"],
+                         "launches": dom["launches"], "dominant_kernel_by_time": by_time,
+                         "mean_op_ms": dom["mean_op_ms"],
+                         "note": "achieved = algorithmic bytes of one operation x operations / sum of CUDA-event time "
+                                 "of all launches of those operations"},
             "kernels": kernels,
+            "rates": {k: v for k, v in rates.items() if v},
             "jtj_multiply": jtj,
             "schur_eliminate": elim,
             "final_cost": recs[-1]["cost"]}
     if world > 1:
-        line["config"]["sharding"] = "points sharded over %d ranks by observation count, cameras replicated; one NCCL all-reduce of the %d-double camera vector per CG iteration" % (world, 9 * rp.C)
+        line["sharding"] = "points sharded over %d ranks by observation count, cameras replicated; one NCCL all-reduce of the %d-double camera vector per CG iteration" % (world, 9 * rp.C)
         if rank != 0:
             gpu.close()
             dist.destroy_process_group()

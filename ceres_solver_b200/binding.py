@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200ba.so")
+# (B200BA_LIB: tooling only -- lets tools/ A/B scripts load a -DB200_DEV_KNOBS build of the same library)
+LIB_PATH = os.environ.get("B200BA_LIB") or os.path.join(_HERE, "libb200ba.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -67,8 +68,8 @@ class LmIteration(C.Structure):
 
 
 class KernelStat(C.Structure):
-    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("device_ms", C.c_double),
-                ("bytes_per_launch", C.c_double)]
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("operations", C.c_int64),
+                ("device_ms", C.c_double), ("bytes_per_operation", C.c_double)]
 
 
 # Every symbol include/b200ba.h declares (tests/test_abi.py checks the library exports all of them).
@@ -307,8 +308,8 @@ class Problem:
         arr = (KernelStat * 32)()
         n = C.c_int()
         _check(lib().b200_stats_get(self.h, arr, 32, C.byref(n)))
-        return {arr[i].name.decode(): dict(launches=arr[i].launches, ms=arr[i].device_ms,
-                                           bytes_per_launch=arr[i].bytes_per_launch) for i in range(n.value)}
+        return {arr[i].name.decode(): dict(launches=arr[i].launches, operations=arr[i].operations, ms=arr[i].device_ms,
+                                           bytes_per_operation=arr[i].bytes_per_operation) for i in range(n.value)}
 
     def total_launches(self):
         return int(lib().b200_total_launches(self.h))

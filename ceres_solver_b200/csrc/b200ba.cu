@@ -280,8 +280,9 @@ struct b200_handle {
   int grid_tile[K_COUNT];
   // stats
   int64_t launches[K_COUNT];
+  int64_t ops[K_COUNT];       // operations: an operation is one logical pass (e.g. one S*x); it may take several launches
   double ms[K_COUNT];
-  double bytes_per_launch[K_COUNT];
+  double bytes_per_op[K_COUNT];
   int64_t h2d_bytes = 0, d2h_bytes = 0;
   bool profiling = false;
   std::vector<EventPair> pending;
@@ -334,8 +335,10 @@ int get_event(b200_handle* h, cudaEvent_t* e) {
 }
 
 // Launch wrapper: counts the launch, optionally brackets it with CUDA events, checks the launch error.
+// primary = false: an auxiliary launch of the same operation (the few >32-row points, the huge points, a helper pass):
+// its time is billed to the operation, which is counted once.
 template <typename F>
-int launch(b200_handle* h, int kid, F&& f) {
+int launch(b200_handle* h, int kid, F&& f, bool primary = true) {
   EventPair ep{};
   if (h->profiling) {
     if (h->pending.size() >= 8192) OK(resolve_events(h));
@@ -348,6 +351,7 @@ int launch(b200_handle* h, int kid, F&& f) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(B200_ERR_CUDA, "launch of %s failed: %s", kKernelNames[kid], cudaGetErrorString(e));
   h->launches[kid]++;
+  if (primary) h->ops[kid]++;
   if (h->profiling) {
     CU(cudaEventRecord(ep.b, h->stream));
     h->pending.push_back(ep);
@@ -432,12 +436,12 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
       a.cost_partial = h->d_tile_partial + num_partials;
       OK(launch(h, K_EVAL_JAC, [&] {
         evaluate_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 2), kTile, smem, h->stream>>>(h->view_big, a);
-      }));
+      }, false));
       num_partials += h->num_big_tiles;
       if (d_sqnorm != nullptr)
         OK(launch(h, K_SQNORM, [&] {
           sqnorm_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, d_sqnorm);
-        }));
+        }, false));
     }
     if (d_sqnorm != nullptr) {
       OK(allreduce_sum(h, d_sqnorm + coff, 9 * static_cast<size_t>(h->C)));
@@ -499,7 +503,7 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
     if (h->num_big_tiles > 0)
       OK(launch(h, K_SCHUR_INIT, [&] {
         schur_init_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view_big, st);
-      }));
+      }, false));
   } else {
     OK(launch(h, K_SCHUR_INIT, [&] {
       schur_init_kernel<<<h->grid_tile[K_SCHUR_INIT], kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view, st);
@@ -508,7 +512,7 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
   if (h->num_huge > 0)
     OK(launch(h, K_SCHUR_INIT, [&] {
       huge_schur_init_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, st);
-    }));
+    }, false));
   OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
   h->cur_b = d_b;
   h->cur_D = d_D;
@@ -541,7 +545,7 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
       OK(launch(h, K_SCHUR_MUL_BIG, [&] {
         schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
             h->view_big, h->d_ete_inv, d_x, d_y, done_flag);
-      }));
+      }, false));
   } else {
     OK(launch(h, K_MISC, [&] {
       diag_sq_mul_kernel<<<flat_grid(h, n, 256), 256, 0, h->stream>>>(n, seed, d_x, d_y, done_flag);
@@ -553,7 +557,7 @@ int schur_mul_dev(b200_handle* h, const double* d_x, double* d_y, const int* don
   if (h->num_huge > 0)
     OK(launch(h, K_SCHUR_MUL_BIG, [&] {
       huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_x, d_y, done_flag);
-    }));
+    }, false));
   return allreduce_sum(h, d_y, n);
 }
 
@@ -566,7 +570,7 @@ int precond_update_dev(b200_handle* h, int type) {
     if (schur)
       OK(launch(h, K_DIAG_BLOCKS, [&] {
         row_q_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, h->d_ete_inv, h->d_q3);
-      }));
+      }, false));
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       const int g = std::max(1, std::min((h->num_cam_items + 7) / 8, h->sm_count * 4));
       if (schur) cam_blocks_kernel<true><<<g, 256, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
@@ -585,7 +589,7 @@ int precond_update_dev(b200_handle* h, int type) {
         const int g = std::min(h->num_big_tiles, h->sm_count);
         if (schur) diag_blocks_kernel<true><<<g, kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view_big, h->d_ete_inv, h->d_upper45);
         else diag_blocks_kernel<false><<<g, kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view_big, h->d_ete_inv, h->d_upper45);
-      }));
+      }, false));
   } else if (type == B200_PRECOND_SCHUR_JACOBI) {
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       diag_blocks_kernel<true><<<h->grid_tile[K_DIAG_BLOCKS], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_ete_inv, h->d_upper45);
@@ -642,7 +646,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       if (h->num_huge > 0)
         OK(launch(h, K_BACKSUB, [&] {
           huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_b, h->d_sol, d_x);
-        }));
+        }, false));
       CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
     }
     return B200_OK;
@@ -706,12 +710,12 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         OK(launch(h, K_SCHUR_MUL_BIG, [&] {
           schur_mul_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 3>(), h->stream>>>(
               h->view_big, h->d_ete_inv, vin, out, &h->d_cg->done);
-        }));
+        }, false));
       }
       if (h->num_huge > 0)
         OK(launch(h, K_SCHUR_MUL_BIG, [&] {
           huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, vin, out, &h->d_cg->done);
-        }));
+        }, false));
       return allreduce_sum(h, out, n);
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
@@ -826,7 +830,7 @@ int dense_schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, 
   if (h->num_huge > 0)
     OK(launch(h, K_BACKSUB, [&] {
       huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, d_b, h->d_sol, d_x);
-    }));
+    }, false));
   CU(cudaMemcpyAsync(d_x + 3 * static_cast<size_t>(h->P), h->d_sol, sizeof(double) * n, cudaMemcpyDeviceToDevice, h->stream));
   return B200_OK;
 }
@@ -1323,7 +1327,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->world = desc->world_size > 1 ? desc->world_size : 1;
   std::memset(h->launches, 0, sizeof(h->launches));
   std::memset(h->ms, 0, sizeof(h->ms));
-  std::memset(h->bytes_per_launch, 0, sizeof(h->bytes_per_launch));
+  std::memset(h->ops, 0, sizeof(h->ops));
+  std::memset(h->bytes_per_op, 0, sizeof(h->bytes_per_op));
   *out = h;  // from here on the caller owns the handle even on failure (b200_destroy is safe on partial state)
   if (desc->stream != nullptr) {
     h->stream = static_cast<cudaStream_t>(desc->stream);
@@ -1512,6 +1517,11 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
             m[32] = static_cast<uint32_t>(wt.row_begin);
             m[33] = static_cast<uint32_t>(wt.pt_begin);
             m[34] = static_cast<uint32_t>(wt.row_count) | (static_cast<uint32_t>(wt.pt_count) << 16);
+            {
+              int maxdeg = 1;   // longest point of the tile (rows): bounds the segmented reductions
+              for (int k = 0; k < wt.pt_count; ++k) maxdeg = std::max(maxdeg, pt_ptr[wt.pt_begin + k + 1] - pt_ptr[wt.pt_begin + k]);
+              m[35] = static_cast<uint32_t>(maxdeg);
+            }
             const int tn = t + w4 * st4;
             if (tn < cta_part[b].y) {
               m[36] = static_cast<uint32_t>(wtiles[tn].row_begin);
@@ -1528,6 +1538,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->v2_mul.per_warp_bytes = v4_per_warp_bytes(st4);
         h->v2_mul.tile_meta = h->d_tile_meta;
         h->v2_mul.stage_x = 1;
+        if (const char* e = dev_env("B200_VARIANT")) h->v2_mul.variant = atoi(e);
         h->mul_smem = v2_sy_bytes(max_cam_span, rep4) + v4_sx_bytes(max_cam_span, 1) + static_cast<size_t>(w4) * h->v2_mul.per_warp_bytes;
         h->mul_v4 = true;
         h->big_folded = dev_env("B200_DISABLE_BIG_FOLD") == nullptr;
@@ -1591,6 +1602,23 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     }
   }
 
+  if (const char* e = dev_env("B200_L2_PERSIST_MB")) {
+    // experiment: keep part of the F cells resident in L2 across the products of a PCG (persisting access window)
+    const size_t want = static_cast<size_t>(atoi(e)) << 20;
+    const size_t lim = std::min<size_t>(want, prop.persistingL2CacheMaxSize);
+    CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim));
+    cudaStreamAttrValue attr{};
+    const size_t fbytes = sizeof(double) * 18 * n;
+    const size_t win = std::min<size_t>(fbytes, prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.base_ptr = h->d_values + 6 * n;
+    attr.accessPolicyWindow.num_bytes = win;
+    attr.accessPolicyWindow.hitRatio = static_cast<float>(std::min(1.0, static_cast<double>(lim) / static_cast<double>(win)));
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    CU(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    fprintf(stderr, "[b200ba] L2 persist: limit %zu MB (max %d MB), window %zu MB (max %d MB), hit ratio %.2f\n", lim >> 20,
+            prop.persistingL2CacheMaxSize >> 20, win >> 20, prop.accessPolicyMaxWindowSize >> 20, attr.accessPolicyWindow.hitRatio);
+  }
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
             "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
@@ -1624,18 +1652,18 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   // Algorithmic (compulsory) bytes per launch, SURVEY §8d with this layout: J values 192 B/row + 4 B camera
   // index per row + 4 B chunk boundary per point, plus the vectors each kernel must read/write once.
   const double Nn = N, Pp = P, Cc = C;
-  h->bytes_per_launch[K_JTJ] = 196 * Nn + 4 * Pp + 24.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_SCHUR_MUL] = 196 * Nn + 52 * Pp + 216 * Cc;
-  h->bytes_per_launch[K_SCHUR_INIT] = 196 * Nn + 16 * Nn + 4 * Pp + 24 * Pp + 48 * Pp + 24 * Pp + 72 * Cc;
-  h->bytes_per_launch[K_DIAG_BLOCKS] = 196 * Nn + 52 * Pp + 360 * Cc;
-  h->bytes_per_launch[K_BACKSUB] = 196 * Nn + 16 * Nn + 52 * Pp + 24 * Pp + 72 * Cc;
-  h->bytes_per_launch[K_EVAL_JAC] = 192 * Nn + 16 * Nn + 16 * Nn + 4 * Nn + 4 * Pp + 2 * 8.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_EVAL_COST] = 16 * Nn + 4 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_SQNORM] = 196 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_SCALE] = 2 * 192 * Nn + 8 * Nn + 8.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_JMUL] = 196 * Nn + 32 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_JTMUL] = 196 * Nn + 16 * Nn + 4 * Pp + 16.0 * (3 * Pp + 9 * Cc);
-  h->bytes_per_launch[K_MODEL_COST] = 196 * Nn + 16 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_JTJ] = 196 * Nn + 4 * Pp + 24.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_SCHUR_MUL] = 196 * Nn + 52 * Pp + 216 * Cc;
+  h->bytes_per_op[K_SCHUR_INIT] = 196 * Nn + 16 * Nn + 4 * Pp + 24 * Pp + 48 * Pp + 24 * Pp + 72 * Cc;
+  h->bytes_per_op[K_DIAG_BLOCKS] = 196 * Nn + 52 * Pp + 360 * Cc;
+  h->bytes_per_op[K_BACKSUB] = 196 * Nn + 16 * Nn + 52 * Pp + 24 * Pp + 72 * Cc;
+  h->bytes_per_op[K_EVAL_JAC] = 192 * Nn + 16 * Nn + 16 * Nn + 4 * Nn + 4 * Pp + 2 * 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_EVAL_COST] = 16 * Nn + 4 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_SQNORM] = 196 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_SCALE] = 2 * 192 * Nn + 8 * Nn + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_JMUL] = 196 * Nn + 32 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_JTMUL] = 196 * Nn + 16 * Nn + 4 * Pp + 16.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_MODEL_COST] = 196 * Nn + 16 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
   return B200_OK;
 }
 
@@ -1789,7 +1817,7 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
     if (h->num_big_tiles > 0)
       OK(launch(h, K_JTJ, [&] {
         jtmul_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, h->d_vp0, dD, h->d_vp1);
-      }));
+      }, false));
     OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
     return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
   }
@@ -1810,7 +1838,7 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
     if (h->num_big_tiles > 0)
       OK(launch(h, K_JTJ, [&] {
         jtmul_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, h->d_vp0, dD, h->d_vp1);
-      }));
+      }, false));
   } else {
     OK(launch(h, K_MISC, [&] {
       diag_sq_mul_kernel<<<flat_grid(h, nc, 256), 256, 0, h->stream>>>(nc, seedD, h->d_vp0 + off, h->d_vp1 + off, nullptr);
@@ -1915,7 +1943,7 @@ int b200_schur_back_substitute(b200_handle* h, const double* z, double* y) {
   if (h->num_huge > 0)
     OK(launch(h, K_BACKSUB, [&] {
       huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, h->cur_b, h->d_xr, h->d_y);
-    }));
+    }, false));
   OK(d2h(h, y, h->d_y, sizeof(double) * 3 * static_cast<size_t>(h->P)));
   std::memcpy(y + 3 * static_cast<size_t>(h->P), z, sizeof(double) * 9 * h->C);
   return B200_OK;
@@ -2217,6 +2245,7 @@ int b200_stats_reset(b200_handle* h) {
   if (h == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
   OK(resolve_events(h));
   std::memset(h->launches, 0, sizeof(h->launches));
+  std::memset(h->ops, 0, sizeof(h->ops));
   std::memset(h->ms, 0, sizeof(h->ms));
   h->h2d_bytes = 0;
   h->d2h_bytes = 0;
@@ -2230,8 +2259,9 @@ int b200_stats_get(b200_handle* h, b200_kernel_stat* out, int max_entries, int* 
     std::memset(&out[n], 0, sizeof(out[n]));
     std::strncpy(out[n].name, kKernelNames[k], sizeof(out[n].name) - 1);
     out[n].launches = h->launches[k];
+    out[n].operations = h->ops[k];
     out[n].device_ms = h->ms[k];
-    out[n].bytes_per_launch = h->bytes_per_launch[k];
+    out[n].bytes_per_operation = h->bytes_per_op[k];
     ++n;
   }
   *num_entries = n;

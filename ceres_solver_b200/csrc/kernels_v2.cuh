@@ -39,6 +39,7 @@ struct V2View {
   int replicas;              // copies of the private camera vector (warp w uses copy w % replicas)
   int direct;                // 1: CTAs RED their (narrow) camera range straight into the output vector; 0: partials
   int per_warp_bytes;
+  int variant;               // development builds only (-DB200_DEV_KNOBS): selects kernel variants for A/B runs; 0 in the product
 };
 
 constexpr int kV2MaxThreads = 384;
@@ -625,7 +626,7 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
     if (lane == 0 && (nxt.z & 0xffffu) != 0u)
       v4_issue(v, ete_inv, stage, c.bars() + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
                static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
-    double t0 = 0.0, t1 = 0.0;
+    double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
     if (active) {
       double xc[9];
       const double* xcp = sx + 9 * (cam - cr.x);
@@ -643,19 +644,51 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
       t1 += f[17] * xc[8];
       t0 += ta;
       t1 += tb;
-      sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
-      sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
-      sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+      w0 = e0.x * t0 + e1.y * t1;
+      w1 = e0.y * t0 + e2.x * t1;
+      w2 = e1.x * t0 + e2.y * t1;
+      if (!(v.variant & 2)) {
+        sW[lane * 3 + 0] = w0;
+        sW[lane * 3 + 1] = w1;
+        sW[lane * 3 + 2] = w2;
+      }
     }
     __syncwarp();
     double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (active) {
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+    if (v.variant & 2) {          // segmented suffix sums by shuffles (log2(longest point) steps), then broadcast
+      const int maxdeg = static_cast<int>(own.w);
+      for (int d = 1; d < maxdeg; d <<= 1) {
+        const double a0 = __shfl_down_sync(0xffffffffu, w0, d), a1 = __shfl_down_sync(0xffffffffu, w1, d),
+                     a2 = __shfl_down_sync(0xffffffffu, w2, d);
+        if (lane + d < sg.end) {
+          w0 += a0;
+          w1 += a1;
+          w2 += a2;
+        }
+      }
+      u0 = __shfl_sync(0xffffffffu, w0, sg.first);
+      u1 = __shfl_sync(0xffffffffu, w1, sg.first);
+      u2 = __shfl_sync(0xffffffffu, w2, sg.first);
+    } else if (v.variant & 1) {          // only the first lane of every point walks its rows; the sum is broadcast by shuffle
+      if (active && lane == sg.first) {
+        for (int j = sg.first; j < sg.end; ++j) {
+          u0 += sW[j * 3 + 0];
+          u1 += sW[j * 3 + 1];
+          u2 += sW[j * 3 + 2];
+        }
+      }
+      u0 = __shfl_sync(0xffffffffu, u0, sg.first);
+      u1 = __shfl_sync(0xffffffffu, u1, sg.first);
+      u2 = __shfl_sync(0xffffffffu, u2, sg.first);
+    } else if (active) {
       for (int j = sg.first; j < sg.end; ++j) {
         u0 += sW[j * 3 + 0];
         u1 += sW[j * 3 + 1];
         u2 += sW[j * 3 + 2];
       }
+    }
+    if (active) {
       const double v0 = -(pa.x * u0 + pa.y * u1 + pb.x * u2);
       const double v1 = -(pa.y * u0 + pb.y * u1 + pc.x * u2);
       const double v2 = -(pb.x * u0 + pc.x * u1 + pc.y * u2);

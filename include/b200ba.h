@@ -182,9 +182,12 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opts, double* state_ino
 /* ---- Instrumentation */
 typedef struct b200_kernel_stat {
   char name[32];
-  int64_t launches;
-  double device_ms;       /* sum of CUDA-event times; only filled while profiling is enabled */
-  double bytes_per_launch;/* algorithmic bytes moved by one launch, 0 if not HBM-bound work */
+  int64_t launches;       /* kernel launches */
+  int64_t operations;     /* logical operations (one S*x, one evaluate ...): an operation may take several launches
+                             (main kernel + the few >32-row points + ...), all billed to it */
+  double device_ms;       /* sum of CUDA-event times of all launches; only filled while profiling is enabled */
+  double bytes_per_operation; /* algorithmic bytes moved by ONE OPERATION, 0 if not HBM-bound work:
+                                 achieved GB/s = bytes_per_operation * operations / device_ms */
 } b200_kernel_stat;
 int b200_profile_enable(b200_handle* h, int on);   /* per-kernel cudaEvent timing on/off (off by default) */
 int b200_stats_reset(b200_handle* h);

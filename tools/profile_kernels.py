@@ -27,8 +27,11 @@ for _ in range(reps):
     gpu.schur_jacobi_update()
     gpu.schur_init(res, D)
     gpu.evaluate(state)
+    gpu.schur_back_substitute(x)
+    gpu.model_cost_change(xf)
 st = gpu.stats()
 for k, v in st.items():
     if v["launches"]:
-        gb = v["bytes_per_launch"] * v["launches"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 and v["bytes_per_launch"] > 0 else float("nan")
-        print("%-28s launches %4d  mean %.4f ms  %8.1f GB/s" % (k, v["launches"], v["ms"] / v["launches"], gb))
+        ops = max(v["operations"], 1)
+        gb = v["bytes_per_operation"] * ops / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 and v["bytes_per_operation"] > 0 else float("nan")
+        print("%-28s launches %4d  operations %4d  mean/op %.4f ms  %8.1f GB/s" % (k, v["launches"], v["operations"], v["ms"] / ops, gb))
