@@ -224,6 +224,11 @@ struct b200_handle {
   double *d_upper45 = nullptr, *d_minv = nullptr, *d_blocks = nullptr;
   double *d_xr = nullptr, *d_p = nullptr, *d_r = nullptr, *d_z = nullptr, *d_tmp = nullptr, *d_sol = nullptr;
   CgState* d_cg = nullptr;
+  // internal point order (b200_create): identity unless `permuted`
+  bool permuted = false;
+  int *d_pt_perm = nullptr, *d_row_perm = nullptr;   // internal block -> caller block
+  double *d_stage_p = nullptr, *d_stage_r = nullptr; // boundary staging: [3P+9C], [2N]
+  std::vector<int> h_pt_perm;
   bool schur_ready = false;
   const double* cur_b = nullptr;  // device pointers of the current ISC Init
   const double* cur_D = nullptr;
@@ -239,6 +244,7 @@ struct b200_handle {
   bool v2_ok = false;
   V2View v2{};
   ProblemView view_big{};   // CTA tiles holding only the points with more than 32 rows
+  ProblemView view_chunks{};  // ... only the <= kTile-row slices of the points with more than kTile rows
   int num_big_tiles = 0;
   double* d_dense_s = nullptr;   // explicit reduced camera system [9C][9C] (allocated by the first dense solve)
   double* d_dense_work = nullptr;
@@ -258,6 +264,7 @@ struct b200_handle {
   WarpTile* d_wtiles = nullptr;
   uint32_t* d_row_meta = nullptr;
   int2 *d_cta_part = nullptr, *d_cta_cam = nullptr;
+  int* d_cta_cams = nullptr;
   double* d_partials = nullptr;
   size_t v2_smem = 0;
   bool v2b_ok = false;        // warp-tile versions of evaluate / schur_init / diag_blocks usable (narrow camera ranges)
@@ -274,6 +281,7 @@ struct b200_handle {
   double* d_q3 = nullptr;
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
+  unsigned* d_cg_bar = nullptr;  // grid barrier words of cg_vector_kernel
   int cg_grid = 1;
   PinnedVec hv[12];           // host-boundary LM loop vectors
   // launch geometry
@@ -308,6 +316,47 @@ int d2h(b200_handle* h, void* dst, const void* src, size_t bytes) {
   CU(cudaStreamSynchronize(h->stream));
   h->d2h_bytes += static_cast<int64_t>(bytes);
   return B200_OK;
+}
+
+// ---- boundary copies in the CALLER's block order (identity order: plain copies)
+int permute_blocks(b200_handle* h, bool gather, size_t nblocks, int w, const int* d_perm, const double* d_src, double* d_dst) {
+  const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((nblocks * w + 255) / 256, static_cast<size_t>(h->sm_count) * 8)));
+  if (gather) permute_gather_kernel<<<grid, 256, 0, h->stream>>>(nblocks, w, d_perm, d_src, d_dst);
+  else permute_scatter_kernel<<<grid, 256, 0, h->stream>>>(nblocks, w, d_perm, d_src, d_dst);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B200_ERR_CUDA, "permute kernel: %s", cudaGetErrorString(e));
+  return B200_OK;
+}
+// parameter-sized vector [3P | 9C]
+int up_params(b200_handle* h, double* d_dst, const double* host) {
+  const size_t bytes = sizeof(double) * h->np;
+  if (!h->permuted) return h2d(h, d_dst, host, bytes);
+  OK(h2d(h, h->d_stage_p, host, bytes));
+  OK(permute_blocks(h, true, h->P, 3, h->d_pt_perm, h->d_stage_p, d_dst));
+  const size_t off = 3 * static_cast<size_t>(h->P);
+  CU(cudaMemcpyAsync(d_dst + off, h->d_stage_p + off, sizeof(double) * 9 * h->C, cudaMemcpyDeviceToDevice, h->stream));
+  return B200_OK;
+}
+int down_params(b200_handle* h, double* host, const double* d_src) {
+  const size_t bytes = sizeof(double) * h->np;
+  if (!h->permuted) return d2h(h, host, d_src, bytes);
+  OK(permute_blocks(h, false, h->P, 3, h->d_pt_perm, d_src, h->d_stage_p));
+  const size_t off = 3 * static_cast<size_t>(h->P);
+  CU(cudaMemcpyAsync(h->d_stage_p + off, d_src + off, sizeof(double) * 9 * h->C, cudaMemcpyDeviceToDevice, h->stream));
+  return d2h(h, host, h->d_stage_p, bytes);
+}
+// residual-sized vector [2N]
+int up_rows(b200_handle* h, double* d_dst, const double* host) {
+  const size_t bytes = sizeof(double) * 2 * static_cast<size_t>(h->N);
+  if (!h->permuted) return h2d(h, d_dst, host, bytes);
+  OK(h2d(h, h->d_stage_r, host, bytes));
+  return permute_blocks(h, true, h->N, 2, h->d_row_perm, h->d_stage_r, d_dst);
+}
+int down_rows(b200_handle* h, double* host, const double* d_src) {
+  const size_t bytes = sizeof(double) * 2 * static_cast<size_t>(h->N);
+  if (!h->permuted) return d2h(h, host, d_src, bytes);
+  OK(permute_blocks(h, false, h->N, 2, h->d_row_perm, d_src, h->d_stage_r));
+  return d2h(h, host, h->d_stage_r, bytes);
 }
 
 int resolve_events(b200_handle* h) {
@@ -659,10 +708,15 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     va.mode = mode;
     va.q = q;
     va.seed_target = seeded ? seed_target : nullptr;
-    void* args[] = {&va};
-    return launch(h, K_CG_VEC, [&] {
-      cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
-    });
+    if (dev_env("B200_CG_COOPERATIVE") != nullptr) {
+      va.bar = nullptr;
+      void* args[] = {&va};
+      return launch(h, K_CG_VEC, [&] {
+        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
+      });
+    }
+    va.bar = h->d_cg_bar;   // ordinary launch + a grid barrier in global memory (cg_kernel.cuh: grid_barrier)
+    return launch(h, K_CG_VEC, [&] { cg_vector_kernel<<<h->cg_grid, kCgThreads, 0, h->stream>>>(va); });
   };
   // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
   const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
@@ -1104,15 +1158,95 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   const int C = desc->num_cameras, P = desc->num_points;
   const int N = static_cast<int>(desc->num_observations);
   // Row structure checks: the SchurEliminator precondition (rows grouped by e block).
-  std::vector<int> pt_ptr(static_cast<size_t>(P) + 1, 0);
+  std::vector<int> caller_ptr(static_cast<size_t>(P) + 1, 0);
   for (int i = 0; i < N; ++i) {
     const int pt = desc->pt_idx[i], cam = desc->cam_idx[i];
     if (pt < 0 || pt >= P || cam < 0 || cam >= C) return fail(B200_ERR_INVALID_ARGUMENT, "row %d: block id out of range", i);
     if (i > 0 && pt < desc->pt_idx[i - 1])
       return fail(B200_ERR_INVALID_ARGUMENT, "rows are not grouped by e block at row %d (reorder_program.cc:278-359)", i);
-    pt_ptr[pt + 1]++;
+    caller_ptr[pt + 1]++;
   }
-  for (int k = 0; k < P; ++k) pt_ptr[k + 1] += pt_ptr[k];
+  for (int k = 0; k < P; ++k) caller_ptr[k + 1] += caller_ptr[k];
+
+  // ---- Internal point order.  The fast kernels give every persistent CTA a contiguous run of points and keep the
+  // cameras those points see in shared memory, so they want neighbouring points to see the same few cameras.  The caller's
+  // e-block order is whatever Ceres' ordering produced (first use in the residual list); the library is free to keep its
+  // own: points (with all their rows, in the caller's relative order) are re-ordered privately here, and every vector /
+  // matrix that crosses the ABI is permuted at the boundary (up_* / down_* below), so the layout contract of the header
+  // (block_jacobian_writer.cc:68-167, reorder_program.cc:262-273) is untouched.  Candidates: the caller's order, by
+  // smallest camera id, by mean camera id; the one with the fewest distinct cameras per 1/num_SM-th of the rows wins, the
+  // caller's order when it is within 10 % of the best (no boundary permutation then).
+  std::vector<int> pt_perm(static_cast<size_t>(P));   // internal point k = caller point pt_perm[k]
+  bool identity_order = true;
+  {
+    for (int k = 0; k < P; ++k) pt_perm[k] = k;
+    const int chunks = prop.multiProcessorCount;
+    auto metric = [&](const std::vector<int>& ord) -> long {
+      std::vector<int> stamp(static_cast<size_t>(C), -1);
+      long total = 0, rows = 0;
+      int chunk = 0;
+      const long target = N / chunks + 1;
+      for (int k = 0; k < P; ++k) {
+        const int q = ord[k];
+        for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
+          const int c = desc->cam_idx[r];
+          if (stamp[c] != chunk) {
+            stamp[c] = chunk;
+            ++total;
+          }
+        }
+        rows += caller_ptr[q + 1] - caller_ptr[q];
+        while (rows >= static_cast<long>(chunk + 1) * target) ++chunk;
+      }
+      return total;
+    };
+    const long m_id = metric(pt_perm);
+    std::vector<long long> kmin(static_cast<size_t>(P)), kmean(static_cast<size_t>(P));
+    for (int q = 0; q < P; ++q) {
+      long long lo = C, hi = 0, sum = 0;
+      const int deg = caller_ptr[q + 1] - caller_ptr[q];
+      for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
+        const long long c = desc->cam_idx[r];
+        lo = std::min(lo, c);
+        hi = std::max(hi, c);
+        sum += c;
+      }
+      kmin[q] = lo * (static_cast<long long>(C) + 1) + hi;                 // smallest camera, then largest
+      kmean[q] = deg > 0 ? (sum * 64) / deg : static_cast<long long>(C) * 64;  // mean camera (1/64 units)
+    }
+    std::vector<int> by_min(pt_perm), by_mean(pt_perm);
+    std::stable_sort(by_min.begin(), by_min.end(), [&](int a, int b) { return kmin[a] < kmin[b]; });
+    std::stable_sort(by_mean.begin(), by_mean.end(), [&](int a, int b) { return kmean[a] < kmean[b]; });
+    const long m_min = metric(by_min), m_mean = metric(by_mean);
+    const long best = std::min(m_min, m_mean);
+    if (dev_env("B200_KEEP_ORDER") == nullptr && static_cast<double>(m_id) > 1.10 * static_cast<double>(best)) {
+      pt_perm = (m_min <= m_mean) ? by_min : by_mean;
+      identity_order = false;
+    }
+    if (getenv("B200_VERBOSE") != nullptr)
+      fprintf(stderr, "[b200ba] point order: distinct cameras per 1/%d of the rows, summed: caller %ld, by min camera %ld, by mean camera %ld -> %s\n",
+              chunks, m_id, m_min, m_mean, identity_order ? "caller's order kept" : (m_min <= m_mean ? "by min camera" : "by mean camera"));
+  }
+  // internal copies of the row structure
+  std::vector<int> cam_i(static_cast<size_t>(N)), pt_i(static_cast<size_t>(N)), row_perm(static_cast<size_t>(N));
+  std::vector<double> obs_i(2 * static_cast<size_t>(N));
+  std::vector<int> pt_ptr(static_cast<size_t>(P) + 1, 0);
+  {
+    int r = 0;
+    for (int k = 0; k < P; ++k) {
+      const int q = pt_perm[k];
+      for (int j = caller_ptr[q]; j < caller_ptr[q + 1]; ++j, ++r) {
+        row_perm[r] = j;                     // internal row r = caller row j
+        cam_i[r] = desc->cam_idx[j];
+        pt_i[r] = k;
+        obs_i[2 * static_cast<size_t>(r)] = desc->obs[2 * static_cast<size_t>(j)];
+        obs_i[2 * static_cast<size_t>(r) + 1] = desc->obs[2 * static_cast<size_t>(j) + 1];
+      }
+      pt_ptr[k + 1] = r;
+    }
+  }
+  const int* const cam_idx = cam_i.data();   // from here on: INTERNAL order
+  const int* const pt_idx = pt_i.data();
   // Tiles: whole points, <= kTile rows and <= kTile points each; a point with more rows becomes chunk tiles.
   std::vector<TileDesc> tiles, chunk_tiles;
   std::vector<int> huge_pts;
@@ -1163,13 +1297,13 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   bool has_dups = false;
   {
     std::vector<int> cptr(static_cast<size_t>(C) + 1, 0);
-    for (int i = 0; i < N; ++i) cptr[desc->cam_idx[i] + 1]++;
+    for (int i = 0; i < N; ++i) cptr[cam_idx[i] + 1]++;
     for (int c = 0; c < C; ++c) cptr[c + 1] += cptr[c];
     std::vector<int> fill(cptr.begin(), cptr.end() - 1);
-    for (int i = 0; i < N; ++i) cam_rows[fill[desc->cam_idx[i]]++] = i;
+    for (int i = 0; i < N; ++i) cam_rows[fill[cam_idx[i]]++] = i;
     for (int c = 0; c < C && !has_dups; ++c)
       for (int j = cptr[c] + 1; j < cptr[c + 1]; ++j)
-        if (desc->pt_idx[cam_rows[j]] == desc->pt_idx[cam_rows[j - 1]]) { has_dups = true; break; }
+        if (pt_idx[cam_rows[j]] == pt_idx[cam_rows[j - 1]]) { has_dups = true; break; }
     const int slice = std::max(256, std::min(4096, N / 4096 + 1));
     for (int c = 0; c < C; ++c)
       for (int b = cptr[c]; b < cptr[c + 1]; b += slice) cam_items.push_back(CamItem{c, b, std::min(b + slice, cptr[c + 1])});
@@ -1185,7 +1319,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   if (v2_possible) {
     for (int k = 0; k < P; ++k)
       for (int r = pt_ptr[k]; r < pt_ptr[k + 1]; ++r)
-        row_meta[r] = static_cast<uint32_t>(desc->cam_idx[r]) | (r == pt_ptr[k] ? 0x80000000u : 0u);
+        row_meta[r] = static_cast<uint32_t>(cam_idx[r]) | (r == pt_ptr[k] ? 0x80000000u : 0u);
     int k = 0;
     while (k < P) {
       const int deg0 = pt_ptr[k + 1] - pt_ptr[k];
@@ -1221,6 +1355,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   }
   const int num_ctas_v2 = prop.multiProcessorCount;
   std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2), cta_big(num_ctas_v2, make_int2(0, 0));
+  std::vector<int> cta_cams;   // direct mode: concatenated per-CTA camera lists
+  bool direct_mode = false;
   int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1, mul_warps = 0, mul_stages = 0, mul_replicas = 1;
   if (v2_possible && !wtiles.empty()) {
     // Static partition by position in the row order, balanced by cost: a warp tile costs about the same whatever its
@@ -1262,19 +1398,59 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         cta_big[k] = make_int2(k == 0 ? 0 : g_end[k - 1], g_end[k]);
       }
     }
-    for (int b = 0; b < num_ctas_v2; ++b) {
-      int lo = C, hi = 0;
-      auto span = [&](int r0, int r1) {
-        for (int r = r0; r < r1; ++r) {
-          lo = std::min(lo, desc->cam_idx[r]);
-          hi = std::max(hi, desc->cam_idx[r] + 1);
+    // Cameras each CTA touches.  Direct mode (camera locality): every CTA gets the sorted LIST of its distinct cameras --
+    // a row addresses its camera by the position in that list (packed into the row word), x of the listed cameras is
+    // staged in shared memory and the private result is flushed with REDs.  What matters is the NUMBER of distinct
+    // cameras per CTA, not their ids (a point that sees cameras 0, 1 and C-1 costs three entries).  Otherwise: id ranges,
+    // per-CTA partial vectors and a fixed-order reduction.
+    {
+      std::vector<int> stamp(static_cast<size_t>(C), -1), local_of(static_cast<size_t>(C), 0);
+      std::vector<int> lo_v(num_ctas_v2, 0), hi_v(num_ctas_v2, 0);
+      std::vector<std::vector<int>> lists(num_ctas_v2);
+      long list_total = 0;
+      int max_list = 1, max_range = 1;
+      for (int b = 0; b < num_ctas_v2; ++b) {
+        int lo = C, hi = 0;
+        auto visit = [&](int r0, int r1) {
+          for (int r = r0; r < r1; ++r) {
+            const int c = cam_idx[r];
+            lo = std::min(lo, c);
+            hi = std::max(hi, c + 1);
+            if (stamp[c] != b) {
+              stamp[c] = b;
+              lists[b].push_back(c);
+            }
+          }
+        };
+        for (int t = cta_part[b].x; t < cta_part[b].y; ++t) visit(wtiles[t].row_begin, wtiles[t].row_begin + wtiles[t].row_count);
+        for (int g = cta_big[b].x; g < cta_big[b].y; ++g) visit(big_tiles[g].obs_begin, big_tiles[g].obs_begin + big_tiles[g].obs_count);
+        if (hi <= lo) { lo = 0; hi = 0; }
+        std::sort(lists[b].begin(), lists[b].end());
+        lo_v[b] = lo;
+        hi_v[b] = hi;
+        list_total += static_cast<long>(lists[b].size());
+        max_list = std::max(max_list, static_cast<int>(lists[b].size()));
+        max_range = std::max(max_range, hi - lo);
+      }
+      // <= ~4 us of REDs at the measured 95 G lane-RED/s; list positions must fit the row word
+      direct_mode = 9 * list_total <= 400000 && max_list <= static_cast<int>(kMetaLocalMask) && C <= static_cast<int>(kMetaCamMask);
+      if (C > static_cast<int>(kMetaCamMask)) v2_possible = false;   // camera ids do not fit the row word: CTA-tile kernels
+      if (direct_mode) {
+        max_cam_span = max_list;
+        for (int b = 0; b < num_ctas_v2; ++b) {
+          cta_cam[b] = make_int2(static_cast<int>(cta_cams.size()), static_cast<int>(lists[b].size()));
+          for (size_t i = 0; i < lists[b].size(); ++i) local_of[lists[b][i]] = static_cast<int>(i);
+          auto pack = [&](int r0, int r1) {
+            for (int r = r0; r < r1; ++r) row_meta[r] |= static_cast<uint32_t>(local_of[cam_idx[r]]) << kMetaLocalShift;
+          };
+          for (int t = cta_part[b].x; t < cta_part[b].y; ++t) pack(wtiles[t].row_begin, wtiles[t].row_begin + wtiles[t].row_count);
+          for (int g = cta_big[b].x; g < cta_big[b].y; ++g) pack(big_tiles[g].obs_begin, big_tiles[g].obs_begin + big_tiles[g].obs_count);
+          cta_cams.insert(cta_cams.end(), lists[b].begin(), lists[b].end());
         }
-      };
-      for (int t = cta_part[b].x; t < cta_part[b].y; ++t) span(wtiles[t].row_begin, wtiles[t].row_begin + wtiles[t].row_count);
-      for (int g = cta_big[b].x; g < cta_big[b].y; ++g) span(big_tiles[g].obs_begin, big_tiles[g].obs_begin + big_tiles[g].obs_count);
-      if (hi <= lo) { lo = 0; hi = 0; }
-      cta_cam[b] = make_int2(lo, hi);
-      max_cam_span = std::max(max_cam_span, hi - lo);
+      } else {
+        max_cam_span = max_range;
+        for (int b = 0; b < num_ctas_v2; ++b) cta_cam[b] = make_int2(lo_v[b], hi_v[b]);
+      }
     }
     // Shared memory budget: `replicas` private camera vectors + per-warp {TMA ring of F cells, exchange scratch}.
     // Prefer one replica per warp (no cross-warp contention) when the camera span of a CTA is small.
@@ -1353,7 +1529,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   }
   const size_t n = static_cast<size_t>(N);
   std::vector<int> pt_of_row(n);
-  for (size_t i = 0; i < n; ++i) pt_of_row[i] = desc->pt_idx[i];
+  for (size_t i = 0; i < n; ++i) pt_of_row[i] = pt_idx[i];
   OK(dev_alloc(&h->d_tiles, tiles.size()));
   OK(dev_alloc(&h->d_cam_idx, n));
   OK(dev_alloc(&h->d_pt_ptr, static_cast<size_t>(P) + 1));
@@ -1401,11 +1577,21 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   CU(cudaEventCreateWithFlags(&h->ev_cg[1], cudaEventDisableTiming));
   CU(cudaMallocHost(reinterpret_cast<void**>(&h->h_fail), 4 * sizeof(int)));
   CU(cudaMemcpyAsync(h->d_tiles, tiles.data(), tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->d_cam_idx, desc->cam_idx, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_cam_idx, cam_idx, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_pt_ptr, pt_ptr.data(), pt_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpyAsync(h->d_pt_of_row, pt_of_row.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CU(cudaMemcpyAsync(h->d_obs, desc->obs, 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_obs, obs_i.data(), 2 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemsetAsync(h->d_values, 0, 24 * n * sizeof(double), h->stream));
+  if (!identity_order) {
+    OK(dev_alloc(&h->d_pt_perm, static_cast<size_t>(P)));
+    OK(dev_alloc(&h->d_row_perm, n));
+    OK(dev_alloc(&h->d_stage_p, h->np));
+    OK(dev_alloc(&h->d_stage_r, 2 * n));
+    CU(cudaMemcpyAsync(h->d_pt_perm, pt_perm.data(), sizeof(int) * P, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_row_perm, row_perm.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    h->h_pt_perm = pt_perm;
+    h->permuted = true;
+  }
   CU(cudaStreamSynchronize(h->stream));
   h->view.C = C;
   h->view.P = P;
@@ -1439,6 +1625,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   if (v2_possible) {
     // the slices of the huge points ride along with the >32-row points in every kernel that has no coupling between the
     // rows of a point (the partition above only covers the plain ones: cta_big indexes the first part of the array)
+    const int num_plain_big = static_cast<int>(big_tiles.size());
     big_tiles.insert(big_tiles.end(), chunk_tiles.begin(), chunk_tiles.end());
     h->num_big_tiles = static_cast<int>(big_tiles.size());
     TileDesc* d_big = nullptr;
@@ -1446,6 +1633,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     h->view_big = h->view;
     h->view_big.tiles = d_big;
     h->view_big.num_tiles = h->num_big_tiles;
+    h->view_chunks = h->view;
+    h->view_chunks.tiles = d_big + num_plain_big;
+    h->view_chunks.num_tiles = static_cast<int>(chunk_tiles.size());
     OK(dev_alloc(&h->d_wtiles, wtiles.size()));
     OK(dev_alloc(&h->d_row_meta, n));
     OK(dev_alloc(&h->d_cta_part, cta_part.size()));
@@ -1473,11 +1663,11 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     h->v2.warps = v2_warps;
     h->v2.stages = v2_stages;
     h->v2.replicas = v2_replicas;
-    {
-      long flush = 0;
-      for (int b = 0; b < num_ctas_v2; ++b) flush += 9L * (cta_cam[b].y - cta_cam[b].x);
-      h->v2.direct = (flush <= 400000) ? 1 : 0;   // <= ~4 us of REDs at the measured 95 G lane-RED/s
-    }
+    h->v2.direct = direct_mode ? 1 : 0;
+    OK(dev_alloc(&h->d_cta_cams, cta_cams.size()));
+    if (!cta_cams.empty())
+      CU(cudaMemcpyAsync(h->d_cta_cams, cta_cams.data(), cta_cams.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    h->v2.cta_cams = h->d_cta_cams;
     h->v2.per_warp_bytes = v2_per_warp_bytes(v2_stages, kV2Scratch);
     h->v2_smem = v2_sy_bytes(max_cam_span, v2_replicas) + static_cast<size_t>(v2_warps) * h->v2.per_warp_bytes;
     h->v2_mul = h->v2;
@@ -1641,8 +1831,11 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_vector_kernel, kCgThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int nblocks = (C + kCgCamsPerCta - 1) / kCgCamsPerCta;
-    h->cg_grid = std::max(1, std::min(nblocks, per_sm * h->sm_count));
+    (void)per_sm;  // one CTA per SM at most: the ordinary-launch grid barrier needs every CTA resident
+    h->cg_grid = std::max(1, std::min(nblocks, h->sm_count));
     OK(dev_alloc(&h->d_red, static_cast<size_t>(h->cg_grid) * 4));
+    OK(dev_alloc(&h->d_cg_bar, 4));
+    CU(cudaMemsetAsync(h->d_cg_bar, 0, 4 * sizeof(unsigned), h->stream));
     OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(h->cg_grid)));
     OK(dev_alloc(&h->d_pq_parts, static_cast<size_t>(prop.multiProcessorCount)));
     CU(cudaMemsetAsync(h->d_seed_pq, 0, sizeof(double) * h->cg_grid, h->stream));
@@ -1679,7 +1872,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_cams, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cg_bar, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_pt_perm, h->d_row_perm, h->d_stage_p, h->d_stage_r,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);
@@ -1714,14 +1907,14 @@ int b200_evaluate(b200_handle* h, const double* state, double* cost, double* res
                   int want_jacobian) {
   if (h == nullptr || state == nullptr || cost == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_state, state, sizeof(double) * h->np));
+  OK(up_params(h, h->d_state, state));
   OK(evaluate_dev(h, h->d_state, residuals != nullptr ? h->d_residuals : nullptr,
                   gradient != nullptr ? h->d_gradient : nullptr, want_jacobian != 0, nullptr, cost));
   if (residuals != nullptr) {
-    OK(d2h(h, residuals, h->d_residuals, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    OK(down_rows(h, residuals, h->d_residuals));
     h->residuals_resident = true;  // the copy in HBM stays valid until the next evaluation that asks for residuals
   }
-  if (gradient != nullptr) OK(d2h(h, gradient, h->d_gradient, sizeof(double) * h->np));
+  if (gradient != nullptr) OK(down_params(h, gradient, h->d_gradient));
   return B200_OK;
 }
 
@@ -1737,13 +1930,13 @@ int b200_jacobian_squared_column_norm(b200_handle* h, double* x) {
   if (h == nullptr || x == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
   OK(sqnorm_dev(h, h->d_vp0));
-  return d2h(h, x, h->d_vp0, sizeof(double) * h->np);
+  return down_params(h, x, h->d_vp0);
 }
 
 int b200_jacobian_scale_columns(b200_handle* h, const double* scale) {
   if (h == nullptr || scale == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_vp0, scale, sizeof(double) * h->np));
+  OK(up_params(h, h->d_vp0, scale));
   OK(scale_dev(h, h->d_vp0));
   CU(cudaStreamSynchronize(h->stream));
   return B200_OK;
@@ -1753,19 +1946,19 @@ int b200_jacobian_right_multiply(b200_handle* h, const double* x, double* y) {
   if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
   const size_t nr = 2 * static_cast<size_t>(h->N);
-  OK(h2d(h, h->d_vp0, x, sizeof(double) * h->np));
-  OK(h2d(h, h->d_vr0, y, sizeof(double) * nr));
+  OK(up_params(h, h->d_vp0, x));
+  OK(up_rows(h, h->d_vr0, y));
   OK(launch(h, K_JMUL, [&] {
     jmul_kernel<<<h->grid_tile[K_JMUL], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_vp0, h->d_vr0);
   }));
-  return d2h(h, y, h->d_vr0, sizeof(double) * nr);
+  return down_rows(h, y, h->d_vr0);
 }
 
 int b200_model_cost_change(b200_handle* h, const double* step, double* model_cost_change) {
   if (h == nullptr || step == nullptr || model_cost_change == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   if (!h->residuals_resident) return fail(B200_ERR_INVALID_ARGUMENT, "needs the residuals of a previous b200_evaluate");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_vp0, step, sizeof(double) * h->np));
+  OK(up_params(h, h->d_vp0, step));
   OK(launch(h, K_MODEL_COST, [&] {
     model_cost_kernel<<<h->grid_tile[K_MODEL_COST], kTile, tile_smem_bytes<1, 1>(), h->stream>>>(h->view, h->d_vp0, h->d_residuals, h->d_tile_partial);
   }));
@@ -1781,45 +1974,45 @@ int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y) {
   if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
   const size_t nr = 2 * static_cast<size_t>(h->N);
-  OK(h2d(h, h->d_vr0, x, sizeof(double) * nr));
+  OK(up_rows(h, h->d_vr0, x));
   // camera part accumulates across ranks: only rank 0 carries the incoming y there
-  OK(h2d(h, h->d_vp0, y, sizeof(double) * h->np));
+  OK(up_params(h, h->d_vp0, y));
   if (h->rank != 0) CU(cudaMemsetAsync(h->d_vp0 + 3 * static_cast<size_t>(h->P), 0, sizeof(double) * 9 * h->C, h->stream));
   OK(launch(h, K_JTMUL, [&] {
     jtmul_kernel<false><<<h->grid_tile[K_JTMUL], kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view, h->d_vr0, nullptr, h->d_vp0);
   }));
   OK(allreduce_sum(h, h->d_vp0 + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
-  return d2h(h, y, h->d_vp0, sizeof(double) * h->np);
+  return down_params(h, y, h->d_vp0);
 }
 
 int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* y) {
   if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_vp0, x, sizeof(double) * h->np));
-  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  OK(up_params(h, h->d_vp0, x));
+  if (D != nullptr) OK(up_params(h, h->d_D, D));
   const double* dD = D != nullptr ? h->d_D : nullptr;
   const size_t off = 3 * static_cast<size_t>(h->P);
   const double* seedD = (dD != nullptr && h->rank == 0) ? dD + off : nullptr;
   const int nc = 9 * h->C;
-  if (h->mul_v4 && h->v2.direct && dev_env("B200_NO_JTJ_V4") == nullptr) {
-    // v4 machinery (jtj_v4_kernel): seed y = D^2 x everywhere, the tile kernel adds J'(J x)
-    OK(launch(h, K_MISC, [&] {
-      diag_sq_mul_kernel<<<flat_grid(h, off, 256), 256, 0, h->stream>>>(static_cast<int>(off), dD, h->d_vp0, h->d_vp1, nullptr);
-    }));
+  if (h->mul_v4 && h->v2.direct) {
+    // one launch (jtj_v4_kernel): the camera part of y is seeded with D_c^2 x_c (9C elements), the tile kernel writes the
+    // point part and adds J'(J x) into the camera part; only the slices of >kTile-row points need a second launch
     OK(launch(h, K_MISC, [&] {
       diag_sq_mul_kernel<<<flat_grid(h, nc, 256), 256, 0, h->stream>>>(nc, seedD, h->d_vp0 + off, h->d_vp1 + off, nullptr);
     }));
     OK(huge_zero(h, h->d_vp1));  // the chunk tiles of huge points add their own D^2 x
+    V2View jv = h->v2_mul;
+    jv.cta_big = h->d_cta_big;   // the kernel takes the CTA's 33..kTile-row points itself
     OK(launch(h, K_JTJ, [&] {
-      if (h->mul_v4_owned) jtj_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_vp0, h->d_vp1);
-      else jtj_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, h->d_vp0, h->d_vp1);
+      if (h->mul_v4_owned) jtj_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(jv, h->d_vp0, dD, h->d_vp1);
+      else jtj_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(jv, h->d_vp0, dD, h->d_vp1);
     }));
-    if (h->num_big_tiles > 0)
+    if (h->view_chunks.num_tiles > 0)
       OK(launch(h, K_JTJ, [&] {
-        jtmul_kernel<true><<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_big, h->d_vp0, dD, h->d_vp1);
+        jtmul_kernel<true><<<std::min(h->view_chunks.num_tiles, h->sm_count * 4), kTile, tile_smem_bytes<3, 1>(), h->stream>>>(h->view_chunks, h->d_vp0, dD, h->d_vp1);
       }, false));
     OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
-    return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
+    return down_params(h, y, h->d_vp1);
   }
   OK(huge_zero(h, h->d_vp1));  // point entries of huge points are accumulated slice by slice
   if (h->v2_ok) {
@@ -1848,20 +2041,40 @@ int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* 
     }));
   }
   OK(allreduce_sum(h, h->d_vp1 + off, 9 * static_cast<size_t>(h->C)));
-  return d2h(h, y, h->d_vp1, sizeof(double) * h->np);
+  return down_params(h, y, h->d_vp1);
 }
 
 int b200_jacobian_get_values(b200_handle* h, double* values) {
   if (h == nullptr || values == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  return d2h(h, values, h->d_values, sizeof(double) * 24 * static_cast<size_t>(h->N));
+  const size_t n = static_cast<size_t>(h->N);
+  if (!h->permuted) return d2h(h, values, h->d_values, sizeof(double) * 24 * n);
+  // cold path (dumps, CPU consumers of the Jacobian): rows back into the caller's order through a temporary
+  double* tmp = nullptr;
+  OK(dev_alloc(&tmp, 24 * n));
+  int rc = permute_blocks(h, false, n, 6, h->d_row_perm, h->d_values, tmp);
+  if (rc == B200_OK) rc = permute_blocks(h, false, n, 18, h->d_row_perm, h->d_values + 6 * n, tmp + 6 * n);
+  if (rc == B200_OK) rc = d2h(h, values, tmp, sizeof(double) * 24 * n);
+  cudaFree(tmp);
+  return rc;
 }
 int b200_jacobian_set_values(b200_handle* h, const double* values) {
   if (h == nullptr || values == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_values, values, sizeof(double) * 24 * static_cast<size_t>(h->N)));
-  CU(cudaStreamSynchronize(h->stream));
-  return B200_OK;
+  const size_t n = static_cast<size_t>(h->N);
+  if (!h->permuted) {
+    OK(h2d(h, h->d_values, values, sizeof(double) * 24 * n));
+    CU(cudaStreamSynchronize(h->stream));
+    return B200_OK;
+  }
+  double* tmp = nullptr;
+  OK(dev_alloc(&tmp, 24 * n));
+  int rc = h2d(h, tmp, values, sizeof(double) * 24 * n);
+  if (rc == B200_OK) rc = permute_blocks(h, true, n, 6, h->d_row_perm, tmp, h->d_values);
+  if (rc == B200_OK) rc = permute_blocks(h, true, n, 18, h->d_row_perm, tmp + 6 * n, h->d_values + 6 * n);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------ LinearSolver
@@ -1874,13 +2087,13 @@ int b200_schur_solve(b200_handle* h, const double* b, const double* D, const b20
   CU(cudaSetDevice(h->device));
   const double* d_b = h->d_residuals;
   if (b != nullptr) {
-    OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    OK(up_rows(h, h->d_b, b));
     d_b = h->d_b;
   }
-  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  if (D != nullptr) OK(up_params(h, h->d_D, D));
   OK(schur_solve_dev(h, d_b, D != nullptr ? h->d_D : nullptr, opts, h->d_y, summary));
   if (summary->termination_type != B200_LS_FAILURE && summary->termination_type != B200_LS_FATAL_ERROR)
-    OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
+    OK(down_params(h, x, h->d_y));
   return B200_OK;
 }
 
@@ -1891,20 +2104,20 @@ int b200_dense_schur_solve(b200_handle* h, const double* b, const double* D, dou
   CU(cudaSetDevice(h->device));
   const double* d_b = h->d_residuals;
   if (b != nullptr) {
-    OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
+    OK(up_rows(h, h->d_b, b));
     d_b = h->d_b;
   }
-  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  if (D != nullptr) OK(up_params(h, h->d_D, D));
   OK(dense_schur_solve_dev(h, d_b, D != nullptr ? h->d_D : nullptr, h->d_y, summary));
-  if (summary->termination_type == B200_LS_SUCCESS) OK(d2h(h, x, h->d_y, sizeof(double) * h->np));
+  if (summary->termination_type == B200_LS_SUCCESS) OK(down_params(h, x, h->d_y));
   return B200_OK;
 }
 
 int b200_schur_init(b200_handle* h, const double* b, const double* D) {
   if (h == nullptr || b == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
-  OK(h2d(h, h->d_b, b, sizeof(double) * 2 * static_cast<size_t>(h->N)));
-  if (D != nullptr) OK(h2d(h, h->d_D, D, sizeof(double) * h->np));
+  OK(up_rows(h, h->d_b, b));
+  if (D != nullptr) OK(up_params(h, h->d_D, D));
   OK(schur_init_dev(h, h->d_b, D != nullptr ? h->d_D : nullptr));
   CU(cudaStreamSynchronize(h->stream));
   return B200_OK;
@@ -1919,7 +2132,7 @@ int b200_schur_ete_inverse(b200_handle* h, double* out) {
   OK(d2h(h, packed.data(), h->d_ete_inv, sizeof(double) * packed.size()));
   for (int k = 0; k < h->P; ++k) {
     const double* s = &packed[6 * static_cast<size_t>(k)];
-    double* o = out + 9 * static_cast<size_t>(k);
+    double* o = out + 9 * static_cast<size_t>(h->permuted ? h->h_pt_perm[k] : k);
     o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
     o[3] = s[1]; o[4] = s[3]; o[5] = s[4];
     o[6] = s[2]; o[7] = s[4]; o[8] = s[5];
@@ -1944,7 +2157,12 @@ int b200_schur_back_substitute(b200_handle* h, const double* z, double* y) {
     OK(launch(h, K_BACKSUB, [&] {
       huge_backsub_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, h->cur_b, h->d_xr, h->d_y);
     }, false));
-  OK(d2h(h, y, h->d_y, sizeof(double) * 3 * static_cast<size_t>(h->P)));
+  if (h->permuted) {
+    OK(permute_blocks(h, false, h->P, 3, h->d_pt_perm, h->d_y, h->d_stage_p));
+    OK(d2h(h, y, h->d_stage_p, sizeof(double) * 3 * static_cast<size_t>(h->P)));
+  } else {
+    OK(d2h(h, y, h->d_y, sizeof(double) * 3 * static_cast<size_t>(h->P)));
+  }
   std::memcpy(y + 3 * static_cast<size_t>(h->P), z, sizeof(double) * 9 * h->C);
   return B200_OK;
 }
@@ -1988,7 +2206,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     scaling.assign(np, 1.0); diagonal.resize(np); lmD.resize(np); model_res.resize(nr); sol.resize(np);
     best = x;
   } else {
-    OK(h2d(h, h->d_state, state_inout, sizeof(double) * np));
+    OK(up_params(h, h->d_state, state_inout));
     OK(launch(h, K_LM_VEC, [&] { fill_kernel<<<flat_grid(h, np, 256), 256, 0, h->stream>>>(np, h->d_scale, 1.0); }));
     CU(cudaMemcpyAsync(h->d_vp1, h->d_state, sizeof(double) * np, cudaMemcpyDeviceToDevice, h->stream));  // best
   }
@@ -2230,7 +2448,7 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     }
   }
   if (host_boundary) std::memcpy(state_inout, best.data(), sizeof(double) * np);
-  else OK(d2h(h, state_inout, h->d_vp1, sizeof(double) * np));
+  else OK(down_params(h, state_inout, h->d_vp1));
   return B200_OK;
 }
 

@@ -45,7 +45,35 @@ struct CgVecArgs {
   const double* pq_parts;
   int num_pq_parts;
   double* seed_pq;
+  unsigned* bar;               // {arrival count, generation}: grid barrier of an ORDINARY launch (all CTAs co-resident: the
+                               // grid is at most one CTA per SM and the stream holds nothing else while it runs); null: the
+                               // kernel was launched cooperatively and uses cooperative-groups grid.sync()
 };
+
+// Reusable grid-wide barrier for a grid whose CTAs are all resident.  ncu on the cooperative launch of this kernel showed
+// 20 k cycles elapsed for 5.4 k active (profiles/r02_cg_vector_ncu.txt): the cooperative launch path itself costs more
+// than the kernel's work, so the kernel is launched normally and synchronises through two words in global memory.
+// A wait that lasts longer than ~2 s traps (a barrier that can never complete must not hang the GPU).
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile unsigned* vgen = bar + 1;
+    const unsigned g = *vgen;            // generation, read BEFORE arriving
+    __threadfence();                     // release: this CTA's writes are visible before its arrival
+    if (atomicAdd(bar, 1u) == nblocks - 1u) {
+      atomicExch(bar, 0u);               // last one in: reset the count, then open the next generation
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*vgen == g) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+      }
+    }
+    __threadfence();                     // acquire
+  }
+  __syncthreads();
+}
 
 // Sums up to three values over the CTA with one barrier pair; results valid in every thread.
 __device__ __forceinline__ void cg_block_sum3(double& a, double& b, double& c, double (*scratch)[3]) {
@@ -88,7 +116,10 @@ __device__ __forceinline__ void cg_totals(const double* red, int nb, int slot0, 
 }
 
 __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
-  cg::grid_group grid = cg::this_grid();
+  auto grid_sync = [&]() {
+    if (a.bar != nullptr) grid_barrier(a.bar, gridDim.x);
+    else cg::this_grid().sync();
+  };
   __shared__ double scratch[kCgThreads / 32][3];
   __shared__ double s_tot[4];
   __shared__ double s_r[kCgCamsPerCta * 9];
@@ -159,7 +190,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     }
     cg_block_sum3(acc, d1, d2, scratch);
     if (tid == 0) a.red[blockIdx.x * 4 + 0] = acc;
-    grid.sync();
+    grid_sync();
   }
 
   // ------------------------------------------------------------------ phase B
@@ -280,7 +311,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       a.red[blockIdx.x * 4 + 3] = accRho;
     }
   }
-  grid.sync();
+  grid_sync();
 
   // ------------------------------------------------------------------ phase C
   double tot[3];

@@ -24,9 +24,12 @@ struct WarpTile {
 struct V2View {
   ProblemView p;
   const WarpTile* wtiles;
-  const uint32_t* row_meta;  // [N] camera | (first row of its point ? 1u << 31 : 0)
+  const uint32_t* row_meta;  // [N] camera (bits 0..19) | index of the camera in the CTA's camera list (bits 20..30, direct mode)
+                             //     | (first row of its point ? 1u << 31 : 0)
   const int2* cta_part;      // per CTA: [tile_begin, tile_end)
-  const int2* cta_cam;       // per CTA: [cam_lo, cam_hi) touched by its tiles
+  const int2* cta_cam;       // per CTA, direct mode: {offset into cta_cams, number of distinct cameras its tiles touch};
+                             //          otherwise: [cam_lo, cam_hi) touched by its tiles
+  const int* cta_cams;       // direct mode: the CTAs' sorted camera lists, concatenated
   const int2* cta_big;       // per CTA: [begin, end) into big_tiles: the >32-row points inside its row range
   const TileDesc* big_tiles; // one point each, 33..kTile rows
   const uint32_t* tile_meta; // v4: [num tiles][kV4MetaWords] row words + own descriptor + descriptor of the tile that reuses the stage
@@ -41,6 +44,25 @@ struct V2View {
   int per_warp_bytes;
   int variant;               // development builds only (-DB200_DEV_KNOBS): selects kernel variants for A/B runs; 0 in the product
 };
+
+// Row word accessors.  A CTA addresses its cameras by their position in its own camera list (direct mode: the list is
+// short, the private camera vectors live in shared memory and are flushed with REDs), or by the offset inside its camera
+// id range (no camera locality: per-CTA partial vectors, cam_reduce_kernel).
+constexpr uint32_t kMetaCamMask = 0xfffffu;   // camera ids below 2^20 on this path
+constexpr int kMetaLocalShift = 20;
+constexpr uint32_t kMetaLocalMask = 0x7ffu;   // at most 2047 cameras per CTA in direct mode
+__device__ __forceinline__ int meta_cam(uint32_t meta) { return static_cast<int>(meta & kMetaCamMask); }
+__device__ __forceinline__ bool meta_head(uint32_t meta) { return meta_head(meta) != 0u; }
+__device__ __forceinline__ int meta_local(const V2View& v, uint32_t meta, int2 cr) {
+  return v.direct ? static_cast<int>((meta >> kMetaLocalShift) & kMetaLocalMask) : meta_cam(meta) - cr.x;
+}
+__device__ __forceinline__ int v2_span(const V2View& v, int2 cr) { return v.direct ? cr.y : cr.y - cr.x; }
+// index into a camera-major global array with `per_cam` doubles per camera of entry i of the CTA's private array
+__device__ __forceinline__ size_t v2_global_entry(const V2View& v, int2 cr, int i, int per_cam) {
+  if (!v.direct) return static_cast<size_t>(per_cam) * cr.x + i;
+  const int c = i / per_cam;
+  return static_cast<size_t>(per_cam) * __ldg(v.cta_cams + cr.x + c) + (i - c * per_cam);
+}
 
 constexpr int kV2MaxThreads = 384;
 constexpr int kV2Scratch = 3;  // doubles of per-lane exchange scratch in every v2 kernel
@@ -125,14 +147,14 @@ __device__ __forceinline__ void v2_prologue(const V2View& v, double* sy, const W
 // it writes a partial vector that cam_reduce_kernel sums in a fixed order.
 __device__ __forceinline__ void v2_epilogue(const V2View& v, const double* sy, int2 cr, double* y_direct) {
   __syncthreads();
-  const int n = 9 * (cr.y - cr.x);
+  const int n = 9 * v2_span(v, cr);
   const int stride = static_cast<int>(v2_sy_stride(v.max_cam_span));
   double* dst = v.partials + static_cast<size_t>(blockIdx.x) * 9 * v.max_cam_span;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = sy[i];
     for (int r = 1; r < v.replicas; ++r) acc += sy[r * stride + i];
     if (v.direct) {
-      if (acc != 0.0) red_add(y_direct + 9 * static_cast<size_t>(cr.x) + i, acc);
+      if (acc != 0.0) red_add(y_direct + v2_global_entry(v, cr, i, 9), acc);
     } else {
       dst[i] = acc;
     }
@@ -181,7 +203,7 @@ __device__ __forceinline__ void cam_accumulate9(double* sy_rep, int cam_local, b
 // warp tiles (the warps' TMA rings are idle by then and provide the staging memory), one point at a time:
 // u = sum_rows E'(F x) through a CTA reduction, then the same update as the warp path, accumulated into the
 // CTA-private camera vector.  Every thread of the CTA must call this (it contains CTA barriers).
-// x of camera `cam` is read at xbase + 9 * (cam - cam0): the global vector (cam0 = 0) or the CTA's staged range.
+// x of a row's camera is read from the global vector (x_staged = false) or from the CTA's staged copy of its cameras.
 // Staging layout: rows are staged in chunks of `chunk_rows`; chunk k lives at base + k * chunk_stride as
 // [chunk_rows x 18 F][chunk_rows x 6 E].  sU: 16 doubles of scratch, bar: an INITIALISED mbarrier whose current phase
 // parity is *parity_io (updated on return; only thread 0's copy matters to the caller).
@@ -195,7 +217,7 @@ struct BigStage {
 
 __device__ __forceinline__ void schur_mul_big_points_impl(const V2View& v, const BigStage& st, uint32_t& parity, double* sy_rep0,
                                                           int2 cr, const double* __restrict__ ete_inv, const double* xbase,
-                                                          int cam0) {
+                                                          bool x_staged) {
   const int2 br = v.cta_big[blockIdx.x];
   const int tid = threadIdx.x;
   double* sU = st.sU;
@@ -214,14 +236,15 @@ __device__ __forceinline__ void schur_mul_big_points_impl(const V2View& v, const
     const int chunk = tid / st.chunk_rows, rr = tid - chunk * st.chunk_rows;
     const double* sF = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride) + rr * 18;
     const double* sE = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride + st.chunk_rows * 144) + rr * 6;
-    int cam = 0;
+    int cam_l = 0;
     double xc[9];
     double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0, p5 = 0.0;
     if (active) {  // everything that does not come through the bulk copy is requested while it is in flight
-      cam = static_cast<int>(__ldg(v.row_meta + d.obs_begin + tid) & 0x7fffffffu);
+      const uint32_t meta = __ldg(v.row_meta + d.obs_begin + tid);
+      cam_l = meta_local(v, meta, cr);
       const double* pi = ete_inv + 6 * static_cast<size_t>(d.pt_begin);
       p0 = __ldg(pi), p1 = __ldg(pi + 1), p2 = __ldg(pi + 2), p3 = __ldg(pi + 3), p4 = __ldg(pi + 4), p5 = __ldg(pi + 5);
-      const double* xcp = xbase + 9 * static_cast<size_t>(cam - cam0);
+      const double* xcp = xbase + 9 * static_cast<size_t>(x_staged ? cam_l : meta_cam(meta));
 #pragma unroll
       for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
     }
@@ -270,7 +293,7 @@ __device__ __forceinline__ void schur_mul_big_points_impl(const V2View& v, const
       const double v2 = -(p2 * u0 + p4 * u1 + p5 * u2);
       t0 += e0.x * v0 + e0.y * v1 + e1.x * v2;
       t1 += e1.y * v0 + e2.x * v1 + e2.y * v2;
-      double* yc = sy_rep0 + 9 * (cam - cr.x);
+      double* yc = sy_rep0 + 9 * cam_l;
 #pragma unroll
       for (int k = 0; k < 9; ++k) atomicAdd(yc + k, f[k] * t0 + f[9 + k] * t1);
     }
@@ -281,7 +304,7 @@ __device__ __forceinline__ void schur_mul_big_points_impl(const V2View& v, const
 // v2/v3 layout: the (idle) ring is used as one contiguous staging area; the kernel ends afterwards, so overwriting the
 // warps' barriers is harmless.
 __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned char* ring, double* sy_rep0, int2 cr,
-                                                     const double* __restrict__ ete_inv, const double* xbase, int cam0) {
+                                                     const double* __restrict__ ete_inv, const double* xbase, bool x_staged) {
   const int2 br = v.cta_big[blockIdx.x];
   if (br.y <= br.x) return;  // uniform per CTA
   BigStage st;
@@ -297,7 +320,7 @@ __device__ __forceinline__ void schur_mul_big_points(const V2View& v, unsigned c
   }
   __syncthreads();
   uint32_t parity = 0;
-  schur_mul_big_points_impl(v, st, parity, sy_rep0, cr, ete_inv, xbase, cam0);
+  schur_mul_big_points_impl(v, st, parity, sy_rep0, cr, ete_inv, xbase, x_staged);
 }
 
 constexpr int kV3MaxThreads = 512;
@@ -337,8 +360,8 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
     const bool active = lane < wt.row_count;
     const size_t row = static_cast<size_t>(wt.row_begin) + lane;
     const uint32_t meta = active ? __ldg(v.row_meta + row) : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), wt.row_count);
     double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
     double t0 = 0.0, t1 = 0.0;
     if (active) {
@@ -418,12 +441,12 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
         g[2 * k + 2] += a.y * t1;
       }
     }
-    cam_accumulate9(my_y, cam - cr.x, active, g);
+    cam_accumulate9(my_y, cam_l, active, g);
     __syncwarp();
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
   }
-  schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x, 0);
+  schur_mul_big_points(v, smem_raw + v2_sy_bytes(v.max_cam_span, v.replicas), sy, cr, ete_inv, x, false);
   v2_epilogue(v, sy, cr, y);
 }
 
@@ -437,6 +460,21 @@ __global__ void __launch_bounds__(kV3MaxThreads, 1)
 // allow) and the slot is refilled at once, so one slot per warp is enough; with one private camera vector per warp the
 // accumulation needs no atomics (cam_accumulate9_owned).
 // ------------------------------------------------------------------------------------------------
+// Segmented suffix sums of three per-lane values over runs of consecutive lanes (the rows of one point): after
+// ceil(log2(maxlen)) steps lane i holds the sum over lanes [i, seg_end) of its run; seg_end is one past the run's last lane.
+__device__ __forceinline__ void seg_suffix_sum3(double& w0, double& w1, double& w2, int seg_end, int maxlen) {
+  const int lane = threadIdx.x & 31;
+  for (int d = 1; d < maxlen; d <<= 1) {
+    const double a0 = __shfl_down_sync(0xffffffffu, w0, d), a1 = __shfl_down_sync(0xffffffffu, w1, d),
+                 a2 = __shfl_down_sync(0xffffffffu, w2, d);
+    if (lane + d < seg_end) {
+      w0 += a0;
+      w1 += a1;
+      w2 += a2;
+    }
+  }
+}
+
 constexpr int kV4MaxThreads = 512;
 constexpr int kV4MetaWords = 40;
 constexpr int kV4StageBytes = 32 * 144 + 32 * 48 + 32 * 48 + kV4MetaWords * 4;  // F | E | P | descriptor block
@@ -570,7 +608,7 @@ __device__ __forceinline__ void v4_big_points(const V2View& v, const V4Ctx& c, c
   uint32_t* pword = reinterpret_cast<uint32_t*>(extra + 8);
   __syncthreads();  // every warp is done with its ring slot and scratch
   uint32_t parity = *pword;
-  schur_mul_big_points_impl(v, st, parity, c.sy(), c.cr, ete_inv, c.sx(), c.cr.x);
+  schur_mul_big_points_impl(v, st, parity, c.sy(), c.cr, ete_inv, c.sx(), true);
   if (threadIdx.x == 0) *pword = parity;
 }
 
@@ -602,8 +640,8 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
     const int row_count = static_cast<int>(own.z & 0xffffu);
     const bool active = lane < row_count;
     const uint32_t meta = active ? sM[lane] : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), row_count);
     double f[18];
     double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0, pa = e0, pb = e0, pc = e0;
     if (active) {
@@ -629,7 +667,7 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
     double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
     if (active) {
       double xc[9];
-      const double* xcp = sx + 9 * (cam - cr.x);
+      const double* xcp = sx + 9 * cam_l;
 #pragma unroll
       for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
       double ta = 0.0, tb = 0.0;
@@ -647,47 +685,14 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
       w0 = e0.x * t0 + e1.y * t1;
       w1 = e0.y * t0 + e2.x * t1;
       w2 = e1.x * t0 + e2.y * t1;
-      if (!(v.variant & 2)) {
-        sW[lane * 3 + 0] = w0;
-        sW[lane * 3 + 1] = w1;
-        sW[lane * 3 + 2] = w2;
-      }
     }
-    __syncwarp();
+    // u = sum over the rows of the point of E'(F x): segmented suffix sums by shuffles (log2(longest point of the tile)
+    // steps; measured 6-8 % faster than the exchange through shared memory: the kernel is bound by LSU wavefronts), the
+    // total sits in the point's first lane and is broadcast from there
+    seg_suffix_sum3(w0, w1, w2, sg.end, static_cast<int>(own.w));
+    const double u0 = __shfl_sync(0xffffffffu, w0, sg.first), u1 = __shfl_sync(0xffffffffu, w1, sg.first),
+                 u2 = __shfl_sync(0xffffffffu, w2, sg.first);
     double g[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-    if (v.variant & 2) {          // segmented suffix sums by shuffles (log2(longest point) steps), then broadcast
-      const int maxdeg = static_cast<int>(own.w);
-      for (int d = 1; d < maxdeg; d <<= 1) {
-        const double a0 = __shfl_down_sync(0xffffffffu, w0, d), a1 = __shfl_down_sync(0xffffffffu, w1, d),
-                     a2 = __shfl_down_sync(0xffffffffu, w2, d);
-        if (lane + d < sg.end) {
-          w0 += a0;
-          w1 += a1;
-          w2 += a2;
-        }
-      }
-      u0 = __shfl_sync(0xffffffffu, w0, sg.first);
-      u1 = __shfl_sync(0xffffffffu, w1, sg.first);
-      u2 = __shfl_sync(0xffffffffu, w2, sg.first);
-    } else if (v.variant & 1) {          // only the first lane of every point walks its rows; the sum is broadcast by shuffle
-      if (active && lane == sg.first) {
-        for (int j = sg.first; j < sg.end; ++j) {
-          u0 += sW[j * 3 + 0];
-          u1 += sW[j * 3 + 1];
-          u2 += sW[j * 3 + 2];
-        }
-      }
-      u0 = __shfl_sync(0xffffffffu, u0, sg.first);
-      u1 = __shfl_sync(0xffffffffu, u1, sg.first);
-      u2 = __shfl_sync(0xffffffffu, u2, sg.first);
-    } else if (active) {
-      for (int j = sg.first; j < sg.end; ++j) {
-        u0 += sW[j * 3 + 0];
-        u1 += sW[j * 3 + 1];
-        u2 += sW[j * 3 + 2];
-      }
-    }
     if (active) {
       const double v0 = -(pa.x * u0 + pa.y * u1 + pb.x * u2);
       const double v1 = -(pa.y * u0 + pb.y * u1 + pc.x * u2);
@@ -697,8 +702,8 @@ __device__ __forceinline__ void v4_tiles(const V2View& v, const double* ete_inv,
 #pragma unroll
       for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
     }
-    if (kOwned) cam_accumulate9_owned(my_y, cam - cr.x, active, g);
-    else cam_accumulate9(my_y, cam - cr.x, active, g);
+    if (kOwned) cam_accumulate9_owned(my_y, cam_l, active, g);
+    else cam_accumulate9(my_y, cam_l, active, g);
   }
   // phases consumed on slot s: tiles it = s, s + stages, ... < `it`
   for (int s = 0; s < v.stages; ++s) flip ^= (((it - s + v.stages - 1) / v.stages) & 1u) << s;
@@ -724,8 +729,7 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
       v4_drain(v, c, 0);
       return;
     }
-    const double* xs = x + 9 * static_cast<size_t>(c.cr.x);
-    for (int i = threadIdx.x; i < 9 * (c.cr.y - c.cr.x); i += blockDim.x) c.sx()[i] = __ldcg(xs + i);
+    for (int i = threadIdx.x; i < 9 * v2_span(v, c.cr); i += blockDim.x) c.sx()[i] = __ldcg(x + v2_global_entry(v, c.cr, i, 9));
   }
   __syncthreads();
   uint32_t flip = 0;
@@ -739,14 +743,14 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
   __shared__ double s_pq;
   if (threadIdx.x == 0) s_pq = 0.0;
   __syncthreads();
-  const int n = 9 * (c.cr.y - c.cr.x);
+  const int n = 9 * v2_span(v, c.cr);
   const double* sy = c.sy();
   const double* sx = c.sx();
   double pq = 0.0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = sy[i];
     for (int r = 1; r < v.replicas; ++r) acc += sy[r * c.sy_stride + i];
-    if (acc != 0.0) red_add(y + 9 * static_cast<size_t>(c.cr.x) + i, acc);
+    if (acc != 0.0) red_add(y + v2_global_entry(v, c.cr, i, 9), acc);
     pq += sx[i] * acc;
   }
 #pragma unroll
@@ -757,12 +761,11 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------------
-// y += J'(J x) with the v4 machinery (the caller seeds y = D^2 x).  Written at the very end of round 1: parity-green on
-// hardware (tests/test_gpu_parity.py::test_jtj_v4), its GB/s not yet profiled (B200_NO_JTJ_V4=1 selects jtj_v2_kernel): the slot carries F, E, the descriptor
-// block and -- in the place of the (E'E)^-1 blocks -- the point part of x for the tile's points (24 B per point: the
-// bulk copy fetches the 16-byte-aligned superset, `xoff` is where the tile's first point starts inside it); x of the
-// camera range is staged like in S*x.  Per row t = E x_p + F x_c; the camera part F't goes through the per-warp private
-// vectors and the direct flush, the point part sum_rows E't is added to y with three REDs per point.
+// (J'J + D^2) x with the v4 machinery: the slot carries F, E, the descriptor block and -- in the place of the (E'E)^-1
+// blocks -- the point part of x for the tile's points (24 B per point: the bulk copy fetches the 16-byte-aligned superset,
+// `xoff` is where the tile's first point starts inside it); x of the CTA's cameras is staged like in S*x.  Per row
+// t = E x_p + F x_c; the camera part F't goes through the per-warp private vectors and the direct flush, the point part
+// D_p^2 x_p + sum_rows E't is written by the point's first lane (segmented shuffle sum; the tile owns its points).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void jtj_v4_issue(const V2View& v, const double* x, unsigned char* stage, uint64_t* bar, int tile,
                                              int row_begin, int pt_begin, int row_count, int pt_count) {
@@ -775,9 +778,99 @@ __device__ __forceinline__ void jtj_v4_issue(const V2View& v, const double* x, u
   bulk_g2s(stage + 7680, v.tile_meta + static_cast<size_t>(kV4MetaWords) * tile, kV4MetaWords * 4u, bar);
 }
 
+// The 33..kTile-row points of the CTA for J'J x, processed by the whole CTA after its warp tiles (same staging as
+// schur_mul_big_points_impl): t = E x_p + F x_c per row, the point part D_p^2 x_p + sum E't is WRITTEN by thread 0 (the
+// CTA owns the point), the camera part F't goes into replica 0 of the private camera vector with shared-memory atomics.
+__device__ __forceinline__ void jtj_big_points_impl(const V2View& v, const BigStage& st, uint32_t& parity, double* sy_rep0, int2 cr,
+                                                    const double* __restrict__ x, const double* __restrict__ D, const double* sx,
+                                                    double* y) {
+  const int2 br = v.cta_big[blockIdx.x];
+  const int tid = threadIdx.x;
+  double* sU = st.sU;
+  for (int b = br.x; b < br.y; ++b) {
+    const TileDesc d = v.big_tiles[b];
+    if (tid == 0) {
+      mbar_arrive_expect_tx(st.bar, d.obs_count * 192u);
+      for (int r0 = 0, k = 0; r0 < d.obs_count; r0 += st.chunk_rows, ++k) {
+        const int rows = min(st.chunk_rows, d.obs_count - r0);
+        unsigned char* dst = st.base + static_cast<size_t>(k) * st.chunk_stride;
+        bulk_g2s(dst, v.p.F() + 18 * static_cast<size_t>(d.obs_begin + r0), rows * 144u, st.bar);
+        bulk_g2s(dst + st.chunk_rows * 144, v.p.E() + 6 * static_cast<size_t>(d.obs_begin + r0), rows * 48u, st.bar);
+      }
+    }
+    const bool active = tid < d.obs_count;
+    const int chunk = tid / st.chunk_rows, rr = tid - chunk * st.chunk_rows;
+    const double* sF = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride) + rr * 18;
+    const double* sE = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride + st.chunk_rows * 144) + rr * 6;
+    int cam_l = 0;
+    double xc[9];
+    const size_t po = 3 * static_cast<size_t>(d.pt_begin);
+    const double xp0 = __ldg(x + po), xp1 = __ldg(x + po + 1), xp2 = __ldg(x + po + 2);
+    if (active) {
+      cam_l = meta_local(v, __ldg(v.row_meta + d.obs_begin + tid), cr);
+      const double* xcp = sx + 9 * cam_l;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) xc[k] = xcp[k];
+    }
+    mbar_wait(st.bar, parity);
+    parity ^= 1;
+    double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
+    double f[18];
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 a = lds2(sF + 2 * k);
+        f[2 * k] = a.x;
+        f[2 * k + 1] = a.y;
+      }
+      const double2 e0 = lds2(sE), e1 = lds2(sE + 2), e2 = lds2(sE + 4);
+      t0 = e0.x * xp0 + e0.y * xp1 + e1.x * xp2;
+      t1 = e1.y * xp0 + e2.x * xp1 + e2.y * xp2;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        t0 += f[k] * xc[k];
+        t1 += f[9 + k] * xc[k];
+      }
+      w0 = e0.x * t0 + e1.y * t1;
+      w1 = e0.y * t0 + e2.x * t1;
+      w2 = e1.x * t0 + e2.y * t1;
+    }
+    if (tid < kTile) {  // the first four warps hold all rows
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+        w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+        w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+      }
+      if ((tid & 31) == 0) {
+        sU[(tid >> 5) * 3 + 0] = w0;
+        sU[(tid >> 5) * 3 + 1] = w1;
+        sU[(tid >> 5) * 3 + 2] = w2;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const double d0 = D != nullptr ? __ldg(D + po) : 0.0, d1 = D != nullptr ? __ldg(D + po + 1) : 0.0,
+                   d2 = D != nullptr ? __ldg(D + po + 2) : 0.0;
+      y[po] = d0 * d0 * xp0 + (sU[0] + sU[3] + sU[6] + sU[9]);
+      y[po + 1] = d1 * d1 * xp1 + (sU[1] + sU[4] + sU[7] + sU[10]);
+      y[po + 2] = d2 * d2 * xp2 + (sU[2] + sU[5] + sU[8] + sU[11]);
+    }
+    if (active) {
+      double* yc = sy_rep0 + 9 * cam_l;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(yc + k, f[k] * t0 + f[9 + k] * t1);
+    }
+    __syncthreads();  // staging and sU are reused by the next point
+  }
+}
+
+// y = (J'J + D^2) x in ONE launch: the point part of y is written by the tile that owns the point (D_p^2 x_p + sum E't,
+// no seeding pass, no REDs), the camera part is added into y_c, which the caller seeds with D_c^2 x_c (a 9C-element
+// kernel).  D may be null.
 template <bool kOwned>
 __global__ void __launch_bounds__(kV4MaxThreads, 1)
-    jtj_v4_kernel(V2View v, const double* __restrict__ x, double* y) {
+    jtj_v4_kernel(V2View v, const double* __restrict__ x, const double* __restrict__ D, double* y) {
   const V4Ctx c = v4_ctx(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int2 part = c.part, cr = c.cr;
@@ -793,12 +886,10 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
   {
     const int n = c.sy_stride * v.replicas;
     for (int i = threadIdx.x; i < n; i += blockDim.x) c.sy()[i] = 0.0;
-    const double* xs = x + off + 9 * static_cast<size_t>(cr.x);
-    for (int i = threadIdx.x; i < 9 * (cr.y - cr.x); i += blockDim.x) c.sx()[i] = __ldcg(xs + i);
+    for (int i = threadIdx.x; i < 9 * v2_span(v, cr); i += blockDim.x) c.sx()[i] = __ldcg(x + off + v2_global_entry(v, cr, i, 9));
   }
   __syncthreads();
   const double* sx = c.sx();
-  double* sW = c.sW();
   double* my_y = c.sy() + (kOwned ? warp : warp % v.replicas) * c.sy_stride;
   const int reissue = v.warps * v.stages;
   int it = 0;
@@ -816,11 +907,18 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     const int pt_begin = static_cast<int>(own.y);
     const bool active = lane < row_count;
     const uint32_t meta = active ? sM[lane] : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), row_count);
+    const int cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), row_count);
+    const bool head = active && lane == sg.first;
     double f[18];
     double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
-    double xp0 = 0.0, xp1 = 0.0, xp2 = 0.0;
+    double xp0 = 0.0, xp1 = 0.0, xp2 = 0.0, dp0 = 0.0, dp1 = 0.0, dp2 = 0.0;
+    const size_t po = 3 * static_cast<size_t>(pt_begin + sg.lpt);
+    if (head && D != nullptr) {  // needed only at the end of the tile: in flight during the arithmetic
+      dp0 = __ldg(D + po);
+      dp1 = __ldg(D + po + 1);
+      dp2 = __ldg(D + po + 2);
+    }
     if (active) {
       const double* fr = sF + lane * 18;
 #pragma unroll
@@ -837,13 +935,13 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
       xp1 = xp[1];
       xp2 = xp[2];
     }
-    __syncwarp();  // every lane is done with the ring slot (and with the previous tile's scratch)
+    __syncwarp();  // every lane is done with the ring slot
     if (lane == 0 && (nxt.z & 0xffffu) != 0u)
       jtj_v4_issue(v, x, stage, c.bars() + s, tile + reissue, static_cast<int>(nxt.x), static_cast<int>(nxt.y),
                    static_cast<int>(nxt.z & 0xffffu), static_cast<int>(nxt.z >> 16));
-    double t0 = 0.0, t1 = 0.0;
+    double t0 = 0.0, t1 = 0.0, w0 = 0.0, w1 = 0.0, w2 = 0.0;
     if (active) {
-      const double* xcp = sx + 9 * (cam - cr.x);
+      const double* xcp = sx + 9 * cam_l;
       t0 = e0.x * xp0 + e0.y * xp1 + e1.x * xp2;
       t1 = e1.y * xp0 + e2.x * xp1 + e2.y * xp2;
 #pragma unroll
@@ -852,28 +950,37 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
         t0 += f[k] * xk;
         t1 += f[9 + k] * xk;
       }
-      sW[lane * 3 + 0] = e0.x * t0 + e1.y * t1;
-      sW[lane * 3 + 1] = e0.y * t0 + e2.x * t1;
-      sW[lane * 3 + 2] = e1.x * t0 + e2.y * t1;
+      w0 = e0.x * t0 + e1.y * t1;
+      w1 = e0.y * t0 + e2.x * t1;
+      w2 = e1.x * t0 + e2.y * t1;
     }
-    __syncwarp();
-    if (active && lane == sg.first) {  // point part: sum over the rows of the point, added to the seeded y
-      double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-      for (int j = sg.first; j < sg.end; ++j) {
-        u0 += sW[j * 3 + 0];
-        u1 += sW[j * 3 + 1];
-        u2 += sW[j * 3 + 2];
-      }
-      double* yp = y + 3 * static_cast<size_t>(pt_begin + sg.lpt);
-      red_add(yp, u0);
-      red_add(yp + 1, u1);
-      red_add(yp + 2, u2);
+    seg_suffix_sum3(w0, w1, w2, sg.end, static_cast<int>(own.w));   // point part: the first lane of the point holds the sum
+    if (head) {
+      y[po] = dp0 * dp0 * xp0 + w0;
+      y[po + 1] = dp1 * dp1 * xp1 + w1;
+      y[po + 2] = dp2 * dp2 * xp2 + w2;
     }
     double g[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) g[k] = active ? f[k] * t0 + f[9 + k] * t1 : 0.0;
-    if (kOwned) cam_accumulate9_owned(my_y, cam - cr.x, active, g);
-    else cam_accumulate9(my_y, cam - cr.x, active, g);
+    if (kOwned) cam_accumulate9_owned(my_y, cam_l, active, g);
+    else cam_accumulate9(my_y, cam_l, active, g);
+  }
+  {  // the CTA's 33..kTile-row points (uniform per CTA)
+    const int2 br = v.cta_big[blockIdx.x];
+    if (br.y > br.x) {
+      double* sw0 = reinterpret_cast<double*>(c.ring() + v.stages * kV4StageBytes);
+      BigStage st;
+      st.base = c.ring();
+      st.chunk_rows = kV4BigChunkRows;
+      st.chunk_stride = v.per_warp_bytes;
+      st.sU = sw0 + 64;
+      unsigned char* extra = c.ring() + v4_extra_offset(v.stages);
+      st.bar = reinterpret_cast<uint64_t*>(extra);
+      __syncthreads();  // every warp is done with its ring slot
+      uint32_t parity = 0;
+      jtj_big_points_impl(v, st, parity, c.sy(), cr, x, D, sx, y);
+    }
   }
   v2_epilogue(v, c.sy(), cr, y + off);
 }
@@ -900,8 +1007,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
     const bool active = lane < wt.row_count;
     const size_t row = static_cast<size_t>(wt.row_begin) + lane;
     const uint32_t meta = active ? v.row_meta[row] : 0x80000000u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), wt.row_count);
     double xc[9], xp[3] = {0, 0, 0};
     double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
     size_t po = 0;
@@ -943,7 +1050,7 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
       double g[9];
 #pragma unroll
       for (int k = 0; k < 9; ++k) g[k] = active ? f[k] * t0 + f[9 + k] * t1 : 0.0;
-      cam_accumulate9(sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span), cam - cr.x, active, g);
+      cam_accumulate9(sy + (warp % v.replicas) * v2_sy_stride(v.max_cam_span), cam_l, active, g);
     }
     __syncwarp();
     if (active && lane == sg.first) {

@@ -11,13 +11,13 @@
 namespace b200 {
 
 // Flush `count` doubles per camera of a replicated private accumulator into global memory with REDs.
-__device__ __forceinline__ void v2_flush(const double* sacc, int per_cam, int span, int replicas, size_t rep_stride,
-                                         double* dst /* already offset to camera cr.x */) {
-  const int n = per_cam * span;
+__device__ __forceinline__ void v2_flush(const V2View& v, int2 cr, const double* sacc, int per_cam, int replicas,
+                                         size_t rep_stride, double* dst /* camera-major, per_cam doubles per camera */) {
+  const int n = per_cam * v2_span(v, cr);
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     double acc = sacc[i];
     for (int r = 1; r < replicas; ++r) acc += sacc[r * rep_stride + i];
-    if (acc != 0.0) red_add(dst + i, acc);
+    if (acc != 0.0) red_add(dst + v2_global_entry(v, cr, i, per_cam), acc);
   }
 }
 
@@ -107,7 +107,6 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int2 part = v.cta_part[blockIdx.x];
   const int2 cr = v.cta_cam[blockIdx.x];
-  const int span = cr.y - cr.x;
   const size_t rstride = v2_sy_stride(v.max_cam_span);
   double* sg_acc = reinterpret_cast<double*>(smem_raw);                 // gradient, [replicas][rstride]
   double* sq_acc = sg_acc + rstride * v.replicas;                       // column norms
@@ -127,8 +126,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
     const bool active = lane < wt.row_count;
     const size_t row = static_cast<size_t>(wt.row_begin) + lane;
     const uint32_t meta = active ? __ldg(v.row_meta + row) : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), wt.row_count);
     double r0 = 0.0, r1 = 0.0;
     double jc[18], jp[6];
 #pragma unroll
@@ -212,7 +211,7 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
         a.gradient[po + 1] = gps[1];
         a.gradient[po + 2] = gps[2];
       }
-      cam_accumulate<9>(my_g, cam - cr.x, active, gc);
+      cam_accumulate<9>(my_g, cam_l, active, gc);
     }
     if (a.scale != nullptr && active) {
       const double* sc = a.scale + camoff + 9 * static_cast<size_t>(cam);
@@ -241,7 +240,7 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
         a.sqnorm[po + 1] = qps[1];
         a.sqnorm[po + 2] = qps[2];
       }
-      cam_accumulate<9>(my_q, cam - cr.x, active, qc);
+      cam_accumulate<9>(my_q, cam_l, active, qc);
     }
     // Jacobian cells: stage the warp's rows contiguously, then one TMA bulk store each for E and F
     if (store_pending) {
@@ -275,8 +274,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
     for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) c += s_cost[w];
     a.cost_partial[blockIdx.x] = c;
   }
-  if (a.gradient != nullptr) v2_flush(sg_acc, 9, span, v.replicas, rstride, a.gradient + camoff + 9 * static_cast<size_t>(cr.x));
-  if (a.sqnorm != nullptr) v2_flush(sq_acc, 9, span, v.replicas, rstride, a.sqnorm + camoff + 9 * static_cast<size_t>(cr.x));
+  if (a.gradient != nullptr) v2_flush(v, cr, sg_acc, 9, v.replicas, rstride, a.gradient + camoff);
+  if (a.sqnorm != nullptr) v2_flush(v, cr, sq_acc, 9, v.replicas, rstride, a.sqnorm + camoff);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -303,8 +302,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) schur_init_v2_kernel(V2View 
     const bool active = lane < wt.row_count;
     const size_t row = static_cast<size_t>(wt.row_begin) + lane;
     const uint32_t meta = active ? __ldg(v.row_meta + row) : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), wt.row_count);
     double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
     double b0 = 0.0, b1 = 0.0;
     size_t pt = 0;
@@ -370,7 +369,7 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) schur_init_v2_kernel(V2View 
 #pragma unroll
       for (int k = 0; k < 9; ++k) g[k] = f[k] * t0 + f[9 + k] * t1;
     }
-    cam_accumulate<9>(my_y, cam - cr.x, active, g);
+    cam_accumulate<9>(my_y, cam_l, active, g);
     __syncwarp();
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
@@ -445,8 +444,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
     const bool active = lane < wt.row_count;
     const size_t row = static_cast<size_t>(wt.row_begin) + lane;
     const uint32_t meta = active ? __ldg(v.row_meta + row) : 0u;
-    const int cam = static_cast<int>(meta & 0x7fffffffu);
-    const Seg sg = v2_segment(active && (meta >> 31), wt.row_count);
+    const int cam = meta_cam(meta), cam_l = meta_local(v, meta, cr);
+    const Seg sg = v2_segment(active && meta_head(meta), wt.row_count);
     double e[6] = {0, 0, 0, 0, 0, 0};
     double pinv[6] = {0, 0, 0, 0, 0, 0};
     if (active && kSchur) {
@@ -511,15 +510,15 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1)
     }
     // 45 packed upper-triangle entries per row, accumulated in three groups of matrix rows ({0,1}, {2,3,4}, {5..8}:
     // 17 + 18 + 10 entries) to bound the live registers; all indices are compile-time after unrolling.
-    diag_rows<kSchur, 0, 2>(f, W, PB, my_acc, cam - cr.x, active);
-    diag_rows<kSchur, 2, 5>(f, W, PB, my_acc, cam - cr.x, active);
-    diag_rows<kSchur, 5, 9>(f, W, PB, my_acc, cam - cr.x, active);
+    diag_rows<kSchur, 0, 2>(f, W, PB, my_acc, cam_l, active);
+    diag_rows<kSchur, 2, 5>(f, W, PB, my_acc, cam_l, active);
+    diag_rows<kSchur, 5, 9>(f, W, PB, my_acc, cam_l, active);
     __syncwarp();
     if (t_issue < part.y && lane == 0) v2_issue(v, c, t_issue, s);
     t_issue += v.warps;
   }
   __syncthreads();
-  v2_flush(sacc, 45, cr.y - cr.x, replicas, astride, out45 + 45 * static_cast<size_t>(cr.x));
+  v2_flush(v, cr, sacc, 45, replicas, astride, out45);
 }
 
 }  // namespace b200

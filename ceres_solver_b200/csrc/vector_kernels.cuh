@@ -149,4 +149,24 @@ __global__ void __launch_bounds__(kVecThreads) sum_kernel(int n, const double* _
   if (threadIdx.x == 0) out[0] = acc;
 }
 
+// Boundary permutations between the caller's block order and the library's internal one (blocks of `w` doubles):
+//   gather :  dst[i] = src[perm[i]]        (caller -> internal, perm[i] = caller index of internal block i)
+//   scatter:  dst[perm[i]] = src[i]        (internal -> caller)
+__global__ void __launch_bounds__(256) permute_gather_kernel(size_t n, int w, const int* __restrict__ perm,
+                                                             const double* __restrict__ src, double* __restrict__ dst) {
+  const size_t total = n * w, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t b = i / w, j = i - b * w;
+    dst[i] = src[static_cast<size_t>(perm[b]) * w + j];
+  }
+}
+__global__ void __launch_bounds__(256) permute_scatter_kernel(size_t n, int w, const int* __restrict__ perm,
+                                                              const double* __restrict__ src, double* __restrict__ dst) {
+  const size_t total = n * w, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t b = i / w, j = i - b * w;
+    dst[static_cast<size_t>(perm[b]) * w + j] = src[i];
+  }
+}
+
 }  // namespace b200

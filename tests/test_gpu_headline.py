@@ -79,24 +79,37 @@ def test_components_match_oracle(case, oracle):
     assert relerr(blocks, diag) < 1e-9
 
 
+@pytest.fixture(scope="module")
+def oracle_traces(case):
+    """The oracle's first three LM iterations, twice: with all host threads and with 7 -- a different summation order in
+    its own products.  The inexact solver amplifies last-bit differences once it runs for 100+ CG iterations on an
+    ill-conditioned reduced system: on ladybug-1723 the oracle's step norm at LM iteration 3 (117 CG iterations) moves by
+    2e-5 between thread counts while iterations 1-2 (4 and 34 CG iterations) agree to 1e-10.  The spread between the two
+    oracle runs is therefore the resolution of the comparison."""
+    out = []
+    for nt in (case.nt, 7 if case.nt != 7 else 5):
+        o = case.orc.default_options()
+        o.num_threads = nt
+        o.max_num_iterations = 3
+        _, recs, _ = case.orc.solve(case.state, o)
+        out.append(recs)
+    return out
+
+
 @pytest.mark.parametrize("host_boundary", [False, True])
-def test_first_lm_iterations_match_oracle(case, host_boundary):
-    """Three LM iterations of bundle_adjuster's configuration from the bench's initial point: same CG iteration
-    counts and accept/reject sequence, cost / step norm / gradient norm to 1e-6 (north_star)."""
-    o = case.orc.default_options()
-    o.num_threads = case.nt
-    o.max_num_iterations = 3
-    _, recs_o, _ = case.orc.solve(case.state, o)
+def test_first_lm_iterations_match_oracle(case, oracle_traces, host_boundary):
+    """Three LM iterations of bundle_adjuster's configuration from the bench's initial point: same CG iteration counts and
+    accept/reject sequence; cost, step norm, gradient norm and radius to north_star's 1e-6 -- or, where the oracle itself
+    cannot reproduce its own numbers to 1e-6 under a change of summation order, to 10x the oracle's own spread (one sample
+    of a noisy quantity), and never looser than 1e-3."""
+    recs_o, recs_o2 = oracle_traces
     _, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(max_num_iterations=3), host_boundary=host_boundary)
-    assert len(recs) == len(recs_o) == 4
-    for a, b in zip(recs, recs_o):
-        # the inexact solver stops on a threshold: a one-iteration difference can only come from last-bit noise in the
-        # stopping test (never seen on these workloads, allowed for robustness); everything else is compared tightly
-        assert abs(a["ls_iterations"] - int(b["ls_iterations"])) <= 1, (a, b)
-        same = a["ls_iterations"] == int(b["ls_iterations"])
-        tol = 1e-6 if same else 1e-3
+    assert len(recs) == len(recs_o) == len(recs_o2) == 4
+    for a, b, b2 in zip(recs, recs_o, recs_o2):
+        assert a["ls_iterations"] == int(b["ls_iterations"]), (a, b)
         assert a["step_is_successful"] == int(b["step_is_successful"])
-        assert abs(a["cost"] - b["cost"]) <= tol * abs(b["cost"]), (a, b)
-        assert abs(a["step_norm"] - b["step_norm"]) <= tol * max(abs(b["step_norm"]), 1e-300), (a, b)
-        assert abs(a["gradient_max_norm"] - b["gradient_max_norm"]) <= 10 * tol * abs(b["gradient_max_norm"]), (a, b)
-        assert abs(a["tr_radius"] - b["tr_radius"]) <= 10 * tol * b["tr_radius"], (a, b)
+        for key, floor in (("cost", 1e-6), ("step_norm", 1e-6), ("gradient_max_norm", 1e-6), ("tr_radius", 1e-6)):
+            ref = float(b[key])
+            spread = abs(float(b2[key]) - ref) / max(abs(ref), 1e-300)
+            tol = min(max(floor, 10.0 * spread), 1e-3)
+            assert abs(a[key] - ref) <= tol * max(abs(ref), 1e-300), (key, a[key], ref, spread, a["iteration"])
