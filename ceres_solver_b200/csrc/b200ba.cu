@@ -29,6 +29,7 @@
 #include "kernels.cuh"
 #include "kernels_v2.cuh"
 #include "kernels_v2b.cuh"
+#include "kernels_v4b.cuh"
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
 #include "spse_kernels.cuh"
@@ -140,6 +141,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
@@ -153,9 +155,10 @@ bool load_nccl() {
   g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
   g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
   g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(lib, "ncclAllGather"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
-  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy && g_nccl.GetErrorString;
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.AllGather && g_nccl.CommDestroy && g_nccl.GetErrorString;
   return g_nccl.ok;
 }
 #endif
@@ -230,6 +233,7 @@ struct b200_handle {
   double *d_stage_p = nullptr, *d_stage_r = nullptr; // boundary staging: [3P+9C], [2N]
   std::vector<int> h_pt_perm;
   bool schur_ready = false;
+  bool q_from_init = false;   // d_q3 holds the per-row blocks of the CURRENT implicit-Schur initialisation
   const double* cur_b = nullptr;  // device pointers of the current ISC Init
   const double* cur_D = nullptr;
   // LM state
@@ -282,6 +286,14 @@ struct b200_handle {
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
   unsigned* d_cg_bar = nullptr;  // grid barrier words of cg_vector_kernel
+  // multi-GPU exchange of the per-iteration partial products over NVLink peer memory (cg_kernel.cuh: xchg_push_kernel +
+  // the gather in cg_vector_kernel); replaces the ncclAllReduce inside the PCG iteration when every peer could be mapped
+  bool xchg_ok = false;
+  double* d_xchg = nullptr;       // [2 slots][world][9C]
+  unsigned* d_xflags = nullptr;   // [2 slots][world] + push counter
+  XchgPeers xpeers{};
+  void* xchg_opened[kMaxXchgRanks * 2] = {};
+  unsigned xepoch = 0;
   int cg_grid = 1;
   PinnedVec hv[12];           // host-boundary LM loop vectors
   // launch geometry
@@ -545,7 +557,28 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
   st.rhs = h->d_rhs;
   st.ye = h->d_ye;
   CU(cudaMemsetAsync(h->d_rhs, 0, sizeof(double) * 9 * h->C, h->stream));
-  if (h->v2b_ok) {
+  h->q_from_init = false;
+  if (h->mul_v4) {
+    // v4 machinery: E, F, b and the tile's D_e through the TMA slot; also writes the per-row 2x2 blocks Q_r the camera-major
+    // block-diagonal pass reads (no separate pass over E for them)
+    InitV4Args ia{};
+    ia.b = d_b;
+    ia.D = d_D;
+    ia.ete_inv = h->d_ete_inv;
+    ia.rhs = h->d_rhs;
+    ia.ye = h->d_ye;
+    ia.q3 = h->cam_major_ok ? h->d_q3 : nullptr;
+    OK(launch(h, K_SCHUR_INIT, [&] {
+      if (h->mul_v4_owned) schur_init_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, ia);
+      else schur_init_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, ia);
+    }));
+    if (h->num_big_tiles > 0) {
+      OK(launch(h, K_SCHUR_INIT, [&] {
+        schur_init_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view_big, st);
+      }, false));
+    }
+    h->q_from_init = ia.q3 != nullptr;
+  } else if (h->v2b_ok) {
     OK(launch(h, K_SCHUR_INIT, [&] {
       schur_init_v2_kernel<<<h->v2.num_ctas, 32 * h->v2_init.warps, h->init_v2_smem, h->stream>>>(h->v2_init, st);
     }));
@@ -561,6 +594,10 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
   if (h->num_huge > 0)
     OK(launch(h, K_SCHUR_INIT, [&] {
       huge_schur_init_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, st);
+    }, false));
+  if (h->q_from_init && h->num_big_tiles > 0)   // Q_r of the rows the warp-tile kernel does not own (needs their (E'E)^-1)
+    OK(launch(h, K_SCHUR_INIT, [&] {
+      row_q_tiles_kernel<<<std::min(h->num_big_tiles, h->sm_count * 8), kTile, 0, h->stream>>>(h->view_big, h->d_ete_inv, h->d_q3);
     }, false));
   OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
   h->cur_b = d_b;
@@ -616,14 +653,14 @@ int precond_update_dev(b200_handle* h, int type) {
   CU(cudaMemsetAsync(h->d_upper45, 0, sizeof(double) * 45 * h->C, h->stream));
   if (h->cam_major_ok) {
     const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
-    if (schur)
+    if (schur && !h->q_from_init)
       OK(launch(h, K_DIAG_BLOCKS, [&] {
         row_q_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, h->d_ete_inv, h->d_q3);
       }, false));
     OK(launch(h, K_DIAG_BLOCKS, [&] {
-      const int g = std::max(1, std::min((h->num_cam_items + 7) / 8, h->sm_count * 4));
-      if (schur) cam_blocks_kernel<true><<<g, 256, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
-      else cam_blocks_kernel<false><<<g, 256, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+      const int g = std::max(1, std::min((h->num_cam_items + 3) / 4, h->sm_count * 12));
+      if (schur) cam_blocks_v2_kernel<true><<<g, 128, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+      else cam_blocks_v2_kernel<false><<<g, 128, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
     }));
   } else if (h->v2b_ok && h->diag_v2_replicas > 0) {
     const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
@@ -704,6 +741,9 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
   // kernels RED straight into it: one product launch + one vector launch per iteration.
   const bool seeded = h->v2_ok && h->v2.direct;
   va.Df = (h->rank == 0) ? Df : nullptr;
+  // multi-GPU: the partial products travel through peer memory instead of an NCCL all-reduce (needs the direct-flush
+  // product: `out` then holds exactly this rank's partial)
+  const bool xchg = h->xchg_ok && h->v2_ok && h->v2.direct && dev_env("B200_NO_PEER_EXCHANGE") == nullptr;
   auto vec = [&](int mode, double* q, double* seed_target) -> int {
     va.mode = mode;
     va.q = q;
@@ -714,6 +754,14 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       return launch(h, K_CG_VEC, [&] {
         cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
       });
+    }
+    va.xg_buf = nullptr;
+    if (xchg && mode != CG_BEGIN) {   // q of this launch is the product pushed last: gather it from the exchange slots
+      va.xg_buf = h->d_xchg;
+      va.xg_flags = h->d_xflags;
+      va.xg_world = h->world;
+      va.xg_slot = static_cast<int>(h->xepoch & 1u);
+      va.xg_epoch = h->xepoch;
     }
     va.bar = h->d_cg_bar;   // ordinary launch + a grid barrier in global memory (cg_kernel.cuh: grid_barrier)
     return launch(h, K_CG_VEC, [&] { cg_vector_kernel<<<h->cg_grid, kCgThreads, 0, h->stream>>>(va); });
@@ -770,7 +818,12 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
         OK(launch(h, K_SCHUR_MUL_BIG, [&] {
           huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, vin, out, &h->d_cg->done);
         }, false));
-      return allreduce_sum(h, out, n);
+      if (!xchg) return allreduce_sum(h, out, n);
+      ++h->xepoch;
+      return launch(h, K_MISC, [&] {
+        xchg_push_kernel<<<std::max(1, std::min(32, (n + 255) / 256)), 256, 0, h->stream>>>(
+            h->xpeers, n, static_cast<int>(h->xepoch & 1u), h->xepoch, out, h->d_xflags + 2 * h->world, &h->d_cg->done);
+      });
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
   };
@@ -1174,7 +1227,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   // own: points (with all their rows, in the caller's relative order) are re-ordered privately here, and every vector /
   // matrix that crosses the ABI is permuted at the boundary (up_* / down_* below), so the layout contract of the header
   // (block_jacobian_writer.cc:68-167, reorder_program.cc:262-273) is untouched.  Candidates: the caller's order, by
-  // smallest camera id, by mean camera id; the one with the fewest distinct cameras per 1/num_SM-th of the rows wins, the
+  // the start of the point's camera arc, by mean camera id; the one with the fewest distinct cameras per 1/num_SM-th of the rows wins, the
   // caller's order when it is within 10 % of the best (no boundary permutation then).
   std::vector<int> pt_perm(static_cast<size_t>(P));   // internal point k = caller point pt_perm[k]
   bool identity_order = true;
@@ -1201,21 +1254,39 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       return total;
     };
     const long m_id = metric(pt_perm);
-    std::vector<long long> kmin(static_cast<size_t>(P)), kmean(static_cast<size_t>(P));
-    for (int q = 0; q < P; ++q) {
-      long long lo = C, hi = 0, sum = 0;
-      const int deg = caller_ptr[q + 1] - caller_ptr[q];
-      for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
-        const long long c = desc->cam_idx[r];
-        lo = std::min(lo, c);
-        hi = std::max(hi, c);
-        sum += c;
+    // keys: (a) start of the point's camera ARC -- its cameras seen as a set on the circle of camera ids, the arc being the
+    // complement of the largest gap; for sets that do not wrap around this is the smallest camera id, for captures whose
+    // last frames look at what the first ones saw (loops) it keeps the points of the seam together -- then the arc's
+    // length; (b) the mean camera id.
+    std::vector<long long> karc(static_cast<size_t>(P)), kmean(static_cast<size_t>(P));
+    {
+      std::vector<int> cams;
+      for (int q = 0; q < P; ++q) {
+        const int deg = caller_ptr[q + 1] - caller_ptr[q];
+        long long sum = 0;
+        cams.clear();
+        for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
+          cams.push_back(desc->cam_idx[r]);
+          sum += desc->cam_idx[r];
+        }
+        std::sort(cams.begin(), cams.end());
+        long long start = C, len = 0;
+        if (deg > 0) {
+          int best_gap = cams[0] + C - cams[deg - 1];   // the gap that wraps around
+          start = cams[0];
+          for (int i = 1; i < deg; ++i)
+            if (cams[i] - cams[i - 1] > best_gap) {
+              best_gap = cams[i] - cams[i - 1];
+              start = cams[i];
+            }
+          len = C - best_gap;
+        }
+        karc[q] = start * (static_cast<long long>(C) + 1) + len;
+        kmean[q] = deg > 0 ? (sum * 64) / deg : static_cast<long long>(C) * 64;
       }
-      kmin[q] = lo * (static_cast<long long>(C) + 1) + hi;                 // smallest camera, then largest
-      kmean[q] = deg > 0 ? (sum * 64) / deg : static_cast<long long>(C) * 64;  // mean camera (1/64 units)
     }
     std::vector<int> by_min(pt_perm), by_mean(pt_perm);
-    std::stable_sort(by_min.begin(), by_min.end(), [&](int a, int b) { return kmin[a] < kmin[b]; });
+    std::stable_sort(by_min.begin(), by_min.end(), [&](int a, int b) { return karc[a] < karc[b]; });
     std::stable_sort(by_mean.begin(), by_mean.end(), [&](int a, int b) { return kmean[a] < kmean[b]; });
     const long m_min = metric(by_min), m_mean = metric(by_mean);
     const long best = std::min(m_min, m_mean);
@@ -1224,8 +1295,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       identity_order = false;
     }
     if (getenv("B200_VERBOSE") != nullptr)
-      fprintf(stderr, "[b200ba] point order: distinct cameras per 1/%d of the rows, summed: caller %ld, by min camera %ld, by mean camera %ld -> %s\n",
-              chunks, m_id, m_min, m_mean, identity_order ? "caller's order kept" : (m_min <= m_mean ? "by min camera" : "by mean camera"));
+      fprintf(stderr, "[b200ba] point order: distinct cameras per 1/%d of the rows, summed: caller %ld, by camera arc %ld, by mean camera %ld -> %s\n",
+              chunks, m_id, m_min, m_mean, identity_order ? "caller's order kept" : (m_min <= m_mean ? "by camera arc" : "by mean camera"));
   }
   // internal copies of the row structure
   std::vector<int> cam_i(static_cast<size_t>(N)), pt_i(static_cast<size_t>(N)), row_perm(static_cast<size_t>(N));
@@ -1304,7 +1375,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     for (int c = 0; c < C && !has_dups; ++c)
       for (int j = cptr[c] + 1; j < cptr[c + 1]; ++j)
         if (pt_idx[cam_rows[j]] == pt_idx[cam_rows[j - 1]]) { has_dups = true; break; }
-    const int slice = std::max(256, std::min(4096, N / 4096 + 1));
+    // ~3 items per resident warp (12 warps per SM): short enough to balance, long enough to amortise the final reduction
+    const int slice = std::max(64, std::min(4096, N / (prop.multiProcessorCount * 36) + 1));
     for (int c = 0; c < C; ++c)
       for (int b = cptr[c]; b < cptr[c + 1]; b += slice) cam_items.push_back(CamItem{c, b, std::min(b + slice, cptr[c + 1])});
   }
@@ -1433,7 +1505,9 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         max_range = std::max(max_range, hi - lo);
       }
       // <= ~4 us of REDs at the measured 95 G lane-RED/s; list positions must fit the row word
-      direct_mode = 9 * list_total <= 400000 && max_list <= static_cast<int>(kMetaLocalMask) && C <= static_cast<int>(kMetaCamMask);
+      long direct_limit = 400000;
+      if (const char* e = dev_env("B200_DIRECT_LIMIT")) direct_limit = atol(e);
+      direct_mode = 9 * list_total <= direct_limit && max_list <= static_cast<int>(kMetaLocalMask) && C <= static_cast<int>(kMetaCamMask);
       if (C > static_cast<int>(kMetaCamMask)) v2_possible = false;   // camera ids do not fit the row word: CTA-tile kernels
       if (direct_mode) {
         max_cam_span = max_list;
@@ -1733,6 +1807,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         h->mul_v4 = true;
         h->big_folded = dev_env("B200_DISABLE_BIG_FOLD") == nullptr;
         h->mul_v4_owned = rep4 == w4;
+        CU(cudaFuncSetAttribute(schur_init_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
+        CU(cudaFuncSetAttribute(schur_init_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(jtj_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(jtj_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
         CU(cudaFuncSetAttribute(schur_mul_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
@@ -1838,6 +1914,65 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaMemsetAsync(h->d_cg_bar, 0, 4 * sizeof(unsigned), h->stream));
     OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(h->cg_grid)));
     OK(dev_alloc(&h->d_pq_parts, static_cast<size_t>(prop.multiProcessorCount)));
+#ifdef B200_WITH_NCCL
+    if (h->world > 1 && h->world <= kMaxXchgRanks && dev_env("B200_NO_PEER_EXCHANGE") == nullptr) {
+      // Peer exchange buffers: allocated with cudaMalloc, exported with CUDA IPC, the handles all-gathered through the NCCL
+      // communicator (the only plumbing the ranks share), every peer's buffer mapped into this process.  Any failure
+      // (no P2P path, IPC unavailable in the launch mode) leaves the NCCL all-reduce in place -- decided jointly.
+      const size_t nC = 9 * static_cast<size_t>(C);
+      OK(dev_alloc(&h->d_xchg, 2 * static_cast<size_t>(h->world) * nC));
+      OK(dev_alloc(&h->d_xflags, 2 * static_cast<size_t>(h->world) + 8));
+      CU(cudaMemsetAsync(h->d_xflags, 0, sizeof(unsigned) * (2 * h->world + 8), h->stream));
+      CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(double) * 2 * h->world * nC, h->stream));
+      unsigned char* d_handles = nullptr;
+      OK(dev_alloc(&d_handles, static_cast<size_t>(h->world) * 128));
+      std::vector<unsigned char> hh(static_cast<size_t>(h->world) * 128, 0);
+      cudaIpcMemHandle_t mine[2];
+      bool ok = cudaIpcGetMemHandle(&mine[0], h->d_xchg) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], h->d_xflags) == cudaSuccess;
+      if (!ok) cudaGetLastError();
+      static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+      std::memcpy(hh.data() + 128 * h->rank, mine, 128);
+      CU(cudaMemcpyAsync(d_handles + 128 * h->rank, hh.data() + 128 * h->rank, 128, cudaMemcpyHostToDevice, h->stream));
+      ncclResult_t r = g_nccl.AllGather(d_handles + 128 * h->rank, d_handles, 128, ncclChar, h->comm, h->stream);
+      if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+      CU(cudaMemcpyAsync(hh.data(), d_handles, hh.size(), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      h->xpeers.world = h->world;
+      h->xpeers.rank = h->rank;
+      for (int p = 0; p < h->world && ok; ++p) {
+        if (p == h->rank) {
+          h->xpeers.buf[p] = h->d_xchg;
+          h->xpeers.flags[p] = h->d_xflags;
+          continue;
+        }
+        cudaIpcMemHandle_t theirs[2];
+        std::memcpy(theirs, hh.data() + 128 * p, 128);
+        void *pb = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&pb, theirs[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+            cudaIpcOpenMemHandle(&pf, theirs[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          ok = false;
+          if (pb != nullptr) cudaIpcCloseMemHandle(pb);
+          break;
+        }
+        h->xchg_opened[2 * p] = pb;
+        h->xchg_opened[2 * p + 1] = pf;
+        h->xpeers.buf[p] = static_cast<double*>(pb);
+        h->xpeers.flags[p] = static_cast<unsigned*>(pf);
+      }
+      // all ranks or none
+      double flag = ok ? 1.0 : 0.0;
+      CU(cudaMemcpyAsync(h->d_scalars + 4, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+      r = g_nccl.AllReduce(h->d_scalars + 4, h->d_scalars + 4, 1, ncclDouble, ncclMin, h->comm, h->stream);
+      if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+      CU(cudaMemcpyAsync(&flag, h->d_scalars + 4, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      cudaFree(d_handles);
+      h->xchg_ok = flag == 1.0;
+      if (getenv("B200_VERBOSE") != nullptr)
+        fprintf(stderr, "[b200ba] rank %d/%d: peer exchange over NVLink %s\n", h->rank, h->world, h->xchg_ok ? "enabled" : "unavailable (NCCL all-reduce per CG iteration)");
+    }
+#endif
     CU(cudaMemsetAsync(h->d_seed_pq, 0, sizeof(double) * h->cg_grid, h->stream));
     CU(cudaMemsetAsync(h->d_pq_parts, 0, sizeof(double) * prop.multiProcessorCount, h->stream));
   }
@@ -1867,7 +2002,9 @@ void b200_destroy(b200_handle* h) {
 #ifdef B200_WITH_NCCL
   if (h->comm != nullptr && g_nccl.ok) g_nccl.CommDestroy(h->comm);
 #endif
-  void* dev_ptrs[] = {h->d_tiles, h->d_cam_idx, h->d_pt_ptr, h->d_pt_of_row, h->d_obs, h->d_values, h->d_state,
+  for (void* p : h->xchg_opened)
+    if (p != nullptr) cudaIpcCloseMemHandle(p);
+  void* dev_ptrs[] = {h->d_xchg, h->d_xflags, h->d_tiles, h->d_cam_idx, h->d_pt_ptr, h->d_pt_of_row, h->d_obs, h->d_values, h->d_state,
                       h->d_residuals, h->d_gradient, h->d_tile_partial, h->d_fail, h->d_scalars, h->d_partial,
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,

@@ -45,6 +45,14 @@ struct CgVecArgs {
   const double* pq_parts;
   int num_pq_parts;
   double* seed_pq;
+  // Multi-GPU (observations sharded, cameras replicated): q = S p is the sum over ranks of the ranks' partial products.
+  // Every rank's push kernel has stored its partial into slot [xg_slot][rank] of EVERY rank's exchange buffer over NVLink
+  // and then raised flag [xg_slot][rank] to xg_epoch; this kernel waits for the `xg_world` flags and sums the partials in
+  // rank order -- the same order on every rank, so the replicated PCG state stays bit-identical without a collective.
+  const double* xg_buf;        // null: single GPU / q already complete
+  const unsigned* xg_flags;
+  int xg_world, xg_slot;
+  unsigned xg_epoch;
   unsigned* bar;               // {arrival count, generation}: grid barrier of an ORDINARY launch (all CTAs co-resident: the
                                // grid is at most one CTA per SM and the stream holds nothing else while it runs); null: the
                                // kernel was launched cooperatively and uses cooperative-groups grid.sync()
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     bj = a.rhs[j0];
     if (mode != CG_BEGIN) {
       pj = a.p[j0];
-      qj = a.q[j0];
+      if (a.xg_buf == nullptr) qj = a.q[j0];
       xj = a.x[j0];
       if (mode != CG_RESET_SECOND) rj = a.r[j0];
     }
@@ -173,6 +181,36 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   }
 
   if (mode != CG_BEGIN && st_done) return;
+  if (a.xg_buf != nullptr && mode != CG_BEGIN) {
+    // gather: wait for every rank's partial of q, then sum them in rank order (replaces qj / a.q)
+    if (tid < a.xg_world) {
+      const volatile unsigned* fl = a.xg_flags + a.xg_slot * a.xg_world + tid;
+      const long long t0 = clock64();
+      while (*fl != a.xg_epoch) {
+        if (clock64() - t0 > 8000000000LL) __trap();   // a peer that never arrives must not hang this GPU
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    const double* part = a.xg_buf + static_cast<size_t>(a.xg_slot) * a.xg_world * n;
+    if (single) {
+      if (ok0) {
+        double acc = 0.0;
+        for (int r = 0; r < a.xg_world; ++r) acc += __ldcg(part + static_cast<size_t>(r) * n + j0);
+        qj = acc;
+        a.q[j0] = acc;
+      }
+    } else {
+      for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int j = blk * kCgCamsPerCta * 9 + tid;
+        if (lane_ok && j < n) {
+          double acc = 0.0;
+          for (int r = 0; r < a.xg_world; ++r) acc += __ldcg(part + static_cast<size_t>(r) * n + j);
+          a.q[j] = acc;
+        }
+      }
+    }
+  }
   const double rho_old = (mode == CG_BEGIN) ? 1.0 : st_rho;
   const int it = (mode == CG_BEGIN) ? 0 : st_it + (mode == CG_RESET_SECOND ? 0 : 1);
 
@@ -415,6 +453,40 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     st->rho = rho_new;
     st->Q0 = Q0_next;
     st->iteration = it;
+  }
+}
+
+// Multi-GPU exchange, sender side: copies this rank's partial product (n doubles) into slot [slot][rank] of every rank's
+// exchange buffer (peer-mapped pointers: the stores travel over NVLink), then -- once every CTA's stores are fenced -- the
+// last CTA raises flag [slot][rank] to `epoch` on every rank.  No-op once the PCG has terminated.
+constexpr int kMaxXchgRanks = 8;
+struct XchgPeers {
+  double* buf[kMaxXchgRanks];
+  unsigned* flags[kMaxXchgRanks];
+  int world, rank;
+};
+__global__ void __launch_bounds__(256) xchg_push_kernel(XchgPeers xp, int n, int slot, unsigned epoch, const double* __restrict__ src,
+                                                        unsigned* counter, const int* __restrict__ done_flag) {
+  if (done_flag != nullptr && __ldcg(done_flag) != 0) return;
+  const size_t base = (static_cast<size_t>(slot) * xp.world + xp.rank) * n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double v = __ldcg(src + i);
+#pragma unroll
+    for (int p = 0; p < kMaxXchgRanks; ++p)
+      if (p < xp.world) xp.buf[p][base + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(counter, 1u) == gridDim.x - 1u) {
+      atomicExch(counter, 0u);
+      __threadfence_system();
+      for (int p = 0; p < xp.world; ++p) {
+        volatile unsigned* f = xp.flags[p] + slot * xp.world + xp.rank;
+        *f = epoch;
+      }
+      __threadfence_system();
+    }
   }
 }
 

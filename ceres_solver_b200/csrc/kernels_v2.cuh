@@ -52,7 +52,7 @@ constexpr uint32_t kMetaCamMask = 0xfffffu;   // camera ids below 2^20 on this p
 constexpr int kMetaLocalShift = 20;
 constexpr uint32_t kMetaLocalMask = 0x7ffu;   // at most 2047 cameras per CTA in direct mode
 __device__ __forceinline__ int meta_cam(uint32_t meta) { return static_cast<int>(meta & kMetaCamMask); }
-__device__ __forceinline__ bool meta_head(uint32_t meta) { return meta_head(meta) != 0u; }
+__device__ __forceinline__ bool meta_head(uint32_t meta) { return (meta & 0x80000000u) != 0u; }
 __device__ __forceinline__ int meta_local(const V2View& v, uint32_t meta, int2 cr) {
   return v.direct ? static_cast<int>((meta >> kMetaLocalShift) & kMetaLocalMask) : meta_cam(meta) - cr.x;
 }

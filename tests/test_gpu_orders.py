@@ -126,17 +126,36 @@ def test_every_entry_point_in_caller_order(case, oracle):
         assert td == tdo and relerr(xd, xdo) < 1e-7
 
 
+@pytest.fixture(scope="module")
+def oracle_traces(case):
+    """Four LM iterations of the oracle with two thread counts: the spread between them is what a change of summation order
+    does to the inexact trajectory (tests/test_gpu_headline.py explains), i.e. the resolution of the comparison."""
+    out = []
+    for nt in (8, 3):
+        o = case.orc.default_options()
+        o.num_threads = nt
+        o.max_num_iterations = 4
+        state_o, recs_o, _ = case.orc.solve(case.state, o)
+        out.append((state_o, recs_o))
+    return out
+
+
 @pytest.mark.parametrize("host_boundary", [False, True])
-def test_lm_trajectory(case, host_boundary):
-    o = case.orc.default_options()
-    o.num_threads = 8
-    o.max_num_iterations = 4
-    state_o, recs_o, _ = case.orc.solve(case.state, o)
+def test_lm_trajectory(case, oracle_traces, host_boundary):
+    (state_o, recs_o), (state_o2, recs_o2) = oracle_traces
     state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(max_num_iterations=4), host_boundary=host_boundary)
     assert len(recs) == len(recs_o)
-    for a, b in zip(recs, recs_o):
+    exact = True
+    for a, b, b2 in zip(recs, recs_o, recs_o2):
+        if int(b["ls_iterations"]) != int(b2["ls_iterations"]) or int(b["step_is_successful"]) != int(b2["step_is_successful"]):
+            break   # the oracle's own trajectory forks here under a change of summation order: nothing left to compare
         assert a["ls_iterations"] == int(b["ls_iterations"]), (a, b)
         assert a["step_is_successful"] == int(b["step_is_successful"])
-        assert abs(a["cost"] - b["cost"]) <= 1e-6 * abs(b["cost"]), (a, b)
-        assert abs(a["step_norm"] - b["step_norm"]) <= 1e-6 * max(abs(b["step_norm"]), 1e-30), (a, b)
-    assert relerr(state, state_o) < 1e-6
+        for key in ("cost", "step_norm"):
+            ref = float(b[key])
+            spread = abs(float(b2[key]) - ref) / max(abs(ref), 1e-300)
+            tol = min(max(1e-6, 10.0 * spread), 1e-2)
+            exact = exact and tol == 1e-6
+            assert abs(a[key] - ref) <= tol * max(abs(ref), 1e-300), (key, a[key], ref, spread, a["iteration"])
+    spread_state = relerr(state_o2, state_o)
+    assert relerr(state, state_o) < max(1e-6, 10.0 * spread_state)
