@@ -37,6 +37,10 @@ void B200Jacobian::LeftMultiplyAndAccumulate(const double* x, double* y) const {
 
 // ---------------------------------------------------------------- B200Evaluator
 std::unique_ptr<Evaluator> B200Evaluator::Create(const Evaluator::Options& options, Program* program, std::string* error) {
+  if (options.evaluation_callback != nullptr) {
+    *error = "B200Evaluator: evaluation callbacks (evaluator.h:72) are not supported on the device path";
+    return nullptr;
+  }
   const int P = options.num_eliminate_blocks;  // e blocks come first in the reduced program (reorder_program.cc:262-273)
   const int C = program->NumParameterBlocks() - P;
   const auto& residual_blocks = program->residual_blocks();
@@ -57,22 +61,37 @@ std::unique_ptr<Evaluator> B200Evaluator::Create(const Evaluator::Options& optio
     const int cam_block = rb->parameter_blocks()[0]->index();  // index in the reduced program
     const int pt_block = rb->parameter_blocks()[1]->index();
     if (pt_block >= P || cam_block < P) {
-      *error = "B200Evaluator: points must form the first elimination group (linear_solver_ordering)";
+      *error = "B200Evaluator: points must form the first elimination group (bundle_adjuster: --ordering_type=user)";
       return nullptr;
     }
     pt_idx[i] = pt_block;
     cam_idx[i] = cam_block - P;
     obs[2 * i] = cost->functor().observed_x;
     obs[2 * i + 1] = cost->functor().observed_y;
+    // every residual block must carry the SAME loss: null, or HuberLoss(a) with one a
+    int this_type = B200_LOSS_TRIVIAL;
+    double this_a = 1.0;
     if (const LossFunction* loss = rb->loss_function()) {
       if (dynamic_cast<const HuberLoss*>(loss) == nullptr) {
         *error = "B200Evaluator: only the trivial and Huber losses are implemented";
         return nullptr;
       }
-      double rho[3];
-      loss->Evaluate(1e8, rho);                 // outlier region: rho' = a / sqrt(s)   (loss_function.cc:52-66)
-      loss_type = B200_LOSS_HUBER;
-      loss_a = rho[1] * 1e4;
+      // HuberLoss(a): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond (loss_function.cc:52-66); two probes deep in the
+      // outlier region recover a whatever its magnitude: rho(4 s) - 2 rho(s) = a^2 there
+      double r1[3], r4[3];
+      double s_probe = 1e30;
+      loss->Evaluate(s_probe, r1);
+      loss->Evaluate(4.0 * s_probe, r4);
+      this_type = B200_LOSS_HUBER;
+      this_a = std::sqrt(r4[0] - 2.0 * r1[0]);
+      if (!(this_a > 0.0) || !std::isfinite(this_a)) this_a = r1[1] * std::sqrt(s_probe);   // rho' = a / sqrt(s)
+    }
+    if (i == 0) {
+      loss_type = this_type;
+      loss_a = this_a;
+    } else if (this_type != loss_type || (this_type == B200_LOSS_HUBER && std::fabs(this_a - loss_a) > 1e-12 * loss_a)) {
+      *error = "B200Evaluator: residual blocks with different loss functions (block " + std::to_string(i) + ")";
+      return nullptr;
     }
   }
   b200_ba_desc desc{};
@@ -105,8 +124,15 @@ std::unique_ptr<SparseMatrix> B200Evaluator::CreateJacobian() const {
   return std::make_unique<B200Jacobian>(bs, ctx_);
 }
 
-bool B200Evaluator::Evaluate(const Evaluator::EvaluateOptions&, const double* state, double* cost, double* residuals,
-                             double* gradient, SparseMatrix* jacobian) {
+bool B200Evaluator::Evaluate(const Evaluator::EvaluateOptions& evaluate_options, const double* state, double* cost,
+                             double* residuals, double* gradient, SparseMatrix* jacobian) {
+  // apply_loss_function = false (evaluator.h:101: Problem::Evaluate and the final cost of Solver::Summary ask for it)
+  // switches the robust correction off on the device; new_evaluation_point only matters to evaluation callbacks
+  if (evaluate_options.apply_loss_function != ctx_->apply_loss_function) {
+    if (!Check(b200_set_apply_loss_function(ctx_->handle, evaluate_options.apply_loss_function ? 1 : 0), "b200_set_apply_loss_function"))
+      return false;
+    ctx_->apply_loss_function = evaluate_options.apply_loss_function;
+  }
   ScopedExecutionTimer total("Evaluator::Total", &execution_summary_);
   ScopedExecutionTimer kind(gradient == nullptr && jacobian == nullptr ? "Evaluator::Residual" : "Evaluator::Jacobian",
                             &execution_summary_);  // the keys Solver::Summary reads (solver.cc:615-628)
@@ -162,30 +188,6 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
   summary.num_iterations = s.num_iterations;
   summary.residual_norm = s.residual_norm;
   summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);  // same numeric order
-  return summary;
-}
-
-// ---------------------------------------------------------------- B200DenseSchurSolver
-LinearSolver::Summary B200DenseSchurSolver::SolveImpl(BlockSparseMatrix* A, const double* b,
-                                                      const LinearSolver::PerSolveOptions& per_solve_options, double* x) {
-  LinearSolver::Summary summary;
-  auto* jac = dynamic_cast<B200Jacobian*>(A);
-  if (jac == nullptr) {
-    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
-    summary.message = "B200DenseSchurSolver needs the Jacobian created by B200Evaluator.";
-    return summary;
-  }
-  b200_solver_summary s{};
-  const double* b_arg = (b == jac->context().last_residuals) ? nullptr : b;
-  if (b200_dense_schur_solve(jac->handle(), b_arg, per_solve_options.D, x, &s) != B200_OK) {
-    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
-    summary.message = b200_last_error();
-    return summary;
-  }
-  summary.num_iterations = s.num_iterations;
-  summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);
-  if (summary.termination_type == LinearSolverTerminationType::FAILURE)
-    summary.message = "Cholesky failure: the reduced camera system is not positive definite.";
   return summary;
 }
 

@@ -7,9 +7,16 @@
 //                                                   (sparse_matrix.h:67-116) forward to the C ABI
 //   B200Evaluator            : Evaluator           evaluator.h:60-168
 //   B200IterativeSchurSolver : BlockSparseMatrixSolver (TypedLinearSolver<BlockSparseMatrix>, linear_solver.h:366-387)
+// (The exact solve on the explicit reduced system, b200_dense_schur_solve, is reachable through the C ABI and the
+//  library's own LM loop; it is not routed through a Ceres factory: SPARSE_SCHUR + CUDA_SPARSE is Ceres' own cuDSS path.)
 //
 // Selected from the unmodified bundle_adjuster CLI with
 //   --linear_solver=iterative_schur --sparse_linear_algebra_library=cuda_sparse --preconditioner=schur_jacobi
+//   --ordering_type=user      (bundle_adjuster's default automatic ordering may put points into the camera group; the device
+//                              path needs the points to be the first elimination group and refuses anything else)
+// The Ceres-side hunks (adapter/ceres_b200.patch, generated and verified by tools/make_adapter_patch.py) drop `final` from
+// BlockSparseMatrix and from the ten virtuals B200Jacobian overrides (block_sparse_matrix.h:60-95) and add one branch to
+// each of the two factories (evaluator.cc:64-70, linear_solver.cc:111-116), both on the SAME predicate (B200Selected).
 #ifndef CERES_INTERNAL_B200_ADAPTER_H_
 #define CERES_INTERNAL_B200_ADAPTER_H_
 
@@ -25,16 +32,22 @@
 
 namespace ceres::internal {
 
+// The one predicate both factory hunks use, so that the evaluator and the linear solver are always selected together.
+inline bool B200Selected(LinearSolverType linear_solver_type, SparseLinearAlgebraLibraryType sparse_library) {
+  return linear_solver_type == ITERATIVE_SCHUR && sparse_library == CUDA_SPARSE;
+}
+
 // Shared owner of the device problem; evaluator, Jacobian and linear solver all point at it.
 struct B200Context {
   b200_handle* handle = nullptr;
   // Host vector the last Evaluate() filled with residuals: when the minimizer hands the same pointer to the linear
   // solver (trust_region_minimizer.cc:399-402) the copy that is still in HBM is used instead of uploading it again.
   const double* last_residuals = nullptr;
+  bool apply_loss_function = true;   // what the device evaluator is currently set to (EvaluateOptions, evaluator.h:101)
   ~B200Context() { b200_destroy(handle); }
 };
 
-class B200Jacobian final : public BlockSparseMatrix {  // needs `final` dropped from block_sparse_matrix.h:60
+class B200Jacobian final : public BlockSparseMatrix {  // ceres_b200.patch drops `final` from the base and its virtuals
  public:
   B200Jacobian(CompressedRowBlockStructure* bs, std::shared_ptr<B200Context> ctx)
       : BlockSparseMatrix(bs), ctx_(std::move(ctx)) {}
@@ -45,18 +58,22 @@ class B200Jacobian final : public BlockSparseMatrix {  // needs `final` dropped 
     return b200_model_cost_change(ctx_->handle, step, model_cost_change) == B200_OK;
   }
 
-  // The four calls TrustRegionMinimizer / LevenbergMarquardtStrategy make on the Jacobian
-  // (trust_region_minimizer.cc:269,277,431; levenberg_marquardt_strategy.cc:84).
-  void SquaredColumnNorm(double* x) const final;
-  void SquaredColumnNorm(double* x, ContextImpl*, int) const final { SquaredColumnNorm(x); }
-  void ScaleColumns(const double* scale) final;
-  void ScaleColumns(const double* scale, ContextImpl*, int) final { ScaleColumns(scale); }
-  void RightMultiplyAndAccumulate(const double* x, double* y) const final;
-  void RightMultiplyAndAccumulate(const double* x, double* y, ContextImpl*, int) const final {
+  // The calls TrustRegionMinimizer / LevenbergMarquardtStrategy make on the Jacobian
+  // (trust_region_minimizer.cc:269,277,431; levenberg_marquardt_strategy.cc:84), threaded overloads included.
+  void SquaredColumnNorm(double* x) const override;
+  void SquaredColumnNorm(double* x, ContextImpl*, int) const override { SquaredColumnNorm(x); }
+  void ScaleColumns(const double* scale) override;
+  void ScaleColumns(const double* scale, ContextImpl*, int) override { ScaleColumns(scale); }
+  void RightMultiplyAndAccumulate(const double* x, double* y) const override;
+  void RightMultiplyAndAccumulate(const double* x, double* y, ContextImpl*, int) const override {
     RightMultiplyAndAccumulate(x, y);
   }
-  void LeftMultiplyAndAccumulate(const double* x, double* y) const final;
-  void SetZero() final {}  // the evaluator overwrites every cell on the device
+  void LeftMultiplyAndAccumulate(const double* x, double* y) const override;
+  void LeftMultiplyAndAccumulate(const double* x, double* y, ContextImpl*, int) const override {
+    LeftMultiplyAndAccumulate(x, y);
+  }
+  void SetZero() override {}  // the evaluator overwrites every cell on the device
+  void SetZero(ContextImpl*, int) override {}
   // CPU consumers (problem dumps, CLUSTER_* preconditioners) pull the values explicitly:
   void SyncValuesToHost() { b200_jacobian_get_values(handle(), mutable_values()); }
 
@@ -91,18 +108,6 @@ class B200Evaluator final : public Evaluator {
 class B200IterativeSchurSolver final : public BlockSparseMatrixSolver {
  public:
   explicit B200IterativeSchurSolver(LinearSolver::Options options) : options_(std::move(options)) {}
-
- private:
-  LinearSolver::Summary SolveImpl(BlockSparseMatrix* A, const double* b,
-                                  const LinearSolver::PerSolveOptions& per_solve_options, double* x) final;
-  LinearSolver::Options options_;
-};
-
-// DENSE_SCHUR / SPARSE_SCHUR on the device: explicit reduced camera system + Cholesky (b200_dense_schur_solve), the exact
-// solve DenseSchurComplementSolver / SparseSchurComplementSolver perform (schur_complement_solver.cc:101-214, :224-408).
-class B200DenseSchurSolver final : public BlockSparseMatrixSolver {
- public:
-  explicit B200DenseSchurSolver(LinearSolver::Options options) : options_(std::move(options)) {}
 
  private:
   LinearSolver::Summary SolveImpl(BlockSparseMatrix* A, const double* b,

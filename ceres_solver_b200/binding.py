@@ -75,7 +75,7 @@ class KernelStat(C.Structure):
 # Every symbol include/b200ba.h declares (tests/test_abi.py checks the library exports all of them).
 SYMBOLS = [
     "b200_nccl_unique_id", "b200_create", "b200_destroy", "b200_last_error", "b200_num_parameters",
-    "b200_num_residuals", "b200_evaluate", "b200_plus", "b200_jacobian_squared_column_norm",
+    "b200_num_residuals", "b200_evaluate", "b200_set_apply_loss_function", "b200_plus", "b200_jacobian_squared_column_norm",
     "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply", "b200_model_cost_change",
     "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_jtj_multiply", "b200_solver_options_default",
     "b200_schur_solve", "b200_dense_schur_solve", "b200_schur_init", "b200_schur_rhs", "b200_schur_ete_inverse", "b200_schur_multiply",
@@ -174,6 +174,9 @@ class Problem:
             return False, float("nan"), res, grad
         _check(rc)
         return True, cost.value, res, grad
+
+    def set_apply_loss_function(self, apply):
+        _check(lib().b200_set_apply_loss_function(self.h, int(bool(apply))))
 
     # ---- Jacobian as a SparseMatrix
     def squared_column_norm(self):

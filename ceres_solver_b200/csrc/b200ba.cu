@@ -205,6 +205,7 @@ struct b200_handle {
   int np = 0;  // 3P + 9C
   int loss_type = 0;
   double loss_a = 1.0;
+  bool apply_loss = true;   // EvaluateOptions::apply_loss_function
   int rank = 0, world = 1;
 #ifdef B200_WITH_NCCL
   ncclComm_t comm = nullptr;
@@ -289,10 +290,9 @@ struct b200_handle {
   // multi-GPU exchange of the per-iteration partial products over NVLink peer memory (cg_kernel.cuh: xchg_push_kernel +
   // the gather in cg_vector_kernel); replaces the ncclAllReduce inside the PCG iteration when every peer could be mapped
   bool xchg_ok = false;
-  double* d_xchg = nullptr;       // [2 slots][world][9C]
-  unsigned* d_xflags = nullptr;   // [2 slots][world] + push counter
+  uint4* d_xchg = nullptr;        // [2 slots][world][9C] packets {lo, epoch, hi, epoch}
   XchgPeers xpeers{};
-  void* xchg_opened[kMaxXchgRanks * 2] = {};
+  void* xchg_opened[kMaxXchgRanks] = {};
   unsigned xepoch = 0;
   int cg_grid = 1;
   PinnedVec hv[12];           // host-boundary LM loop vectors
@@ -466,7 +466,7 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
   a.cost_partial = h->d_tile_partial;
   a.scale = d_scale;
   a.fail_flag = h->d_fail;
-  a.loss_type = h->loss_type;
+  a.loss_type = h->apply_loss ? h->loss_type : B200_LOSS_TRIVIAL;
   a.loss_a = h->loss_a;
   if (sqnorm_done != nullptr) *sqnorm_done = false;
   CU(cudaMemsetAsync(h->d_fail, 0, sizeof(int), h->stream));
@@ -485,7 +485,7 @@ int evaluate_dev(b200_handle* h, const double* d_state, double* d_residuals, dou
     e.cost_partial = h->d_tile_partial;
     e.scale = d_scale;
     e.fail_flag = h->d_fail;
-    e.loss_type = h->loss_type;
+    e.loss_type = a.loss_type;
     e.loss_a = h->loss_a;
     if (d_sqnorm != nullptr) CU(cudaMemsetAsync(d_sqnorm + coff, 0, sizeof(double) * 9 * h->C, h->stream));
     if (d_sqnorm != nullptr) OK(huge_zero(h, d_sqnorm));
@@ -569,14 +569,11 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
     ia.ye = h->d_ye;
     ia.q3 = h->cam_major_ok ? h->d_q3 : nullptr;
     OK(launch(h, K_SCHUR_INIT, [&] {
-      if (h->mul_v4_owned) schur_init_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, ia);
-      else schur_init_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(h->v2_mul, ia);
+      V2View iv = h->v2_mul;
+      iv.cta_big = h->d_cta_big;   // the kernel takes the CTA's 33..kTile-row points itself
+      if (h->mul_v4_owned) schur_init_v4_kernel<true><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(iv, ia);
+      else schur_init_v4_kernel<false><<<h->v2.num_ctas, 32 * h->v2_mul.warps, h->mul_smem, h->stream>>>(iv, ia);
     }));
-    if (h->num_big_tiles > 0) {
-      OK(launch(h, K_SCHUR_INIT, [&] {
-        schur_init_kernel<<<std::min(h->num_big_tiles, h->sm_count * 4), kTile, tile_smem_bytes<9, 3>(), h->stream>>>(h->view_big, st);
-      }, false));
-    }
     h->q_from_init = ia.q3 != nullptr;
   } else if (h->v2b_ok) {
     OK(launch(h, K_SCHUR_INIT, [&] {
@@ -595,9 +592,9 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
     OK(launch(h, K_SCHUR_INIT, [&] {
       huge_schur_init_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, st);
     }, false));
-  if (h->q_from_init && h->num_big_tiles > 0)   // Q_r of the rows the warp-tile kernel does not own (needs their (E'E)^-1)
+  if (h->q_from_init && h->view_chunks.num_tiles > 0)   // Q_r of the slices of the huge points (needs their (E'E)^-1)
     OK(launch(h, K_SCHUR_INIT, [&] {
-      row_q_tiles_kernel<<<std::min(h->num_big_tiles, h->sm_count * 8), kTile, 0, h->stream>>>(h->view_big, h->d_ete_inv, h->d_q3);
+      row_q_tiles_kernel<<<std::min(h->view_chunks.num_tiles, h->sm_count * 8), kTile, 0, h->stream>>>(h->view_chunks, h->d_ete_inv, h->d_q3);
     }, false));
   OK(allreduce_sum(h, h->d_rhs, 9 * static_cast<size_t>(h->C)));
   h->cur_b = d_b;
@@ -659,8 +656,9 @@ int precond_update_dev(b200_handle* h, int type) {
       }, false));
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       const int g = std::max(1, std::min((h->num_cam_items + 3) / 4, h->sm_count * 12));
-      if (schur) cam_blocks_v2_kernel<true><<<g, 128, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
-      else cam_blocks_v2_kernel<false><<<g, 128, 0, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+      const size_t smem = static_cast<size_t>(kCamBlkThreads / 32) * kCamBlkWarpBytes;
+      if (schur) cam_blocks_v2_kernel<true><<<g, kCamBlkThreads, smem, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
+      else cam_blocks_v2_kernel<false><<<g, kCamBlkThreads, smem, h->stream>>>(h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_upper45);
     }));
   } else if (h->v2b_ok && h->diag_v2_replicas > 0) {
     const bool schur = type == B200_PRECOND_SCHUR_JACOBI;
@@ -748,23 +746,21 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     va.mode = mode;
     va.q = q;
     va.seed_target = seeded ? seed_target : nullptr;
-    if (dev_env("B200_CG_COOPERATIVE") != nullptr) {
-      va.bar = nullptr;
-      void* args[] = {&va};
-      return launch(h, K_CG_VEC, [&] {
-        cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
-      });
-    }
-    va.xg_buf = nullptr;
-    if (xchg && mode != CG_BEGIN) {   // q of this launch is the product pushed last: gather it from the exchange slots
-      va.xg_buf = h->d_xchg;
-      va.xg_flags = h->d_xflags;
-      va.xg_world = h->world;
+    va.xg.world = 0;
+    if (xchg && mode != CG_BEGIN) {   // q of this launch is this rank's partial product: exchange + sum inside the kernel
+      va.xg = h->xpeers;
       va.xg_slot = static_cast<int>(h->xepoch & 1u);
       va.xg_epoch = h->xepoch;
     }
-    va.bar = h->d_cg_bar;   // ordinary launch + a grid barrier in global memory (cg_kernel.cuh: grid_barrier)
-    return launch(h, K_CG_VEC, [&] { cg_vector_kernel<<<h->cg_grid, kCgThreads, 0, h->stream>>>(va); });
+    va.bar = nullptr;
+    if (dev_env("B200_CG_SOFT_BARRIER") != nullptr) {   // A/B: ordinary launch + grid barrier in global memory (3 % slower)
+      va.bar = h->d_cg_bar;
+      return launch(h, K_CG_VEC, [&] { cg_vector_kernel<<<h->cg_grid, kCgThreads, 0, h->stream>>>(va); });
+    }
+    void* args[] = {&va};
+    return launch(h, K_CG_VEC, [&] {
+      cudaLaunchCooperativeKernel(reinterpret_cast<void*>(cg_vector_kernel), dim3(h->cg_grid), dim3(kCgThreads), args, 0, h->stream);
+    });
   };
   // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
   const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
@@ -819,11 +815,8 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
           huge_schur_mul_kernel<<<huge_grid(h), kHugeThreads, 0, h->stream>>>(h->view, h->num_huge, h->d_huge_pts, h->d_ete_inv, vin, out, &h->d_cg->done);
         }, false));
       if (!xchg) return allreduce_sum(h, out, n);
-      ++h->xepoch;
-      return launch(h, K_MISC, [&] {
-        xchg_push_kernel<<<std::max(1, std::min(32, (n + 255) / 256)), 256, 0, h->stream>>>(
-            h->xpeers, n, static_cast<int>(h->xepoch & 1u), h->xepoch, out, h->d_xflags + 2 * h->world, &h->d_cg->done);
-      });
+      ++h->xepoch;   // the vector kernel that consumes this product exchanges it under this epoch
+      return B200_OK;
     }
     return schur_mul_dev(h, vin, out, &h->d_cg->done);
   };
@@ -1678,6 +1671,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->view.obs = h->d_obs;
   h->view.values = h->d_values;
 
+  CU(cudaFuncSetAttribute(cam_blocks_v2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamBlkThreads / 32) * kCamBlkWarpBytes));
+  CU(cudaFuncSetAttribute(cam_blocks_v2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (kCamBlkThreads / 32) * kCamBlkWarpBytes));
   if (!has_dups && dev_env("B200_DISABLE_CAM_MAJOR") == nullptr) {
     h->num_cam_items = static_cast<int>(cam_items.size());
     OK(dev_alloc(&h->d_cam_items, cam_items.size()));
@@ -1921,19 +1916,17 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       // (no P2P path, IPC unavailable in the launch mode) leaves the NCCL all-reduce in place -- decided jointly.
       const size_t nC = 9 * static_cast<size_t>(C);
       OK(dev_alloc(&h->d_xchg, 2 * static_cast<size_t>(h->world) * nC));
-      OK(dev_alloc(&h->d_xflags, 2 * static_cast<size_t>(h->world) + 8));
-      CU(cudaMemsetAsync(h->d_xflags, 0, sizeof(unsigned) * (2 * h->world + 8), h->stream));
-      CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(double) * 2 * h->world * nC, h->stream));
+      CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(uint4) * 2 * h->world * nC, h->stream));   // epoch 0 is never used
       unsigned char* d_handles = nullptr;
-      OK(dev_alloc(&d_handles, static_cast<size_t>(h->world) * 128));
-      std::vector<unsigned char> hh(static_cast<size_t>(h->world) * 128, 0);
-      cudaIpcMemHandle_t mine[2];
-      bool ok = cudaIpcGetMemHandle(&mine[0], h->d_xchg) == cudaSuccess && cudaIpcGetMemHandle(&mine[1], h->d_xflags) == cudaSuccess;
+      OK(dev_alloc(&d_handles, static_cast<size_t>(h->world) * 64));
+      std::vector<unsigned char> hh(static_cast<size_t>(h->world) * 64, 0);
+      cudaIpcMemHandle_t mine;
+      bool ok = cudaIpcGetMemHandle(&mine, h->d_xchg) == cudaSuccess;
       if (!ok) cudaGetLastError();
       static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-      std::memcpy(hh.data() + 128 * h->rank, mine, 128);
-      CU(cudaMemcpyAsync(d_handles + 128 * h->rank, hh.data() + 128 * h->rank, 128, cudaMemcpyHostToDevice, h->stream));
-      ncclResult_t r = g_nccl.AllGather(d_handles + 128 * h->rank, d_handles, 128, ncclChar, h->comm, h->stream);
+      std::memcpy(hh.data() + 64 * h->rank, &mine, 64);
+      CU(cudaMemcpyAsync(d_handles + 64 * h->rank, hh.data() + 64 * h->rank, 64, cudaMemcpyHostToDevice, h->stream));
+      ncclResult_t r = g_nccl.AllGather(d_handles + 64 * h->rank, d_handles, 64, ncclChar, h->comm, h->stream);
       if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(r));
       CU(cudaMemcpyAsync(hh.data(), d_handles, hh.size(), cudaMemcpyDeviceToHost, h->stream));
       CU(cudaStreamSynchronize(h->stream));
@@ -1942,23 +1935,18 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       for (int p = 0; p < h->world && ok; ++p) {
         if (p == h->rank) {
           h->xpeers.buf[p] = h->d_xchg;
-          h->xpeers.flags[p] = h->d_xflags;
           continue;
         }
-        cudaIpcMemHandle_t theirs[2];
-        std::memcpy(theirs, hh.data() + 128 * p, 128);
-        void *pb = nullptr, *pf = nullptr;
-        if (cudaIpcOpenMemHandle(&pb, theirs[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&pf, theirs[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaIpcMemHandle_t theirs;
+        std::memcpy(&theirs, hh.data() + 64 * p, 64);
+        void* pb = nullptr;
+        if (cudaIpcOpenMemHandle(&pb, theirs, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
           cudaGetLastError();
           ok = false;
-          if (pb != nullptr) cudaIpcCloseMemHandle(pb);
           break;
         }
-        h->xchg_opened[2 * p] = pb;
-        h->xchg_opened[2 * p + 1] = pf;
-        h->xpeers.buf[p] = static_cast<double*>(pb);
-        h->xpeers.flags[p] = static_cast<unsigned*>(pf);
+        h->xchg_opened[p] = pb;
+        h->xpeers.buf[p] = static_cast<uint4*>(pb);
       }
       // all ranks or none
       double flag = ok ? 1.0 : 0.0;
@@ -2004,7 +1992,7 @@ void b200_destroy(b200_handle* h) {
 #endif
   for (void* p : h->xchg_opened)
     if (p != nullptr) cudaIpcCloseMemHandle(p);
-  void* dev_ptrs[] = {h->d_xchg, h->d_xflags, h->d_tiles, h->d_cam_idx, h->d_pt_ptr, h->d_pt_of_row, h->d_obs, h->d_values, h->d_state,
+  void* dev_ptrs[] = {h->d_xchg, h->d_tiles, h->d_cam_idx, h->d_pt_ptr, h->d_pt_of_row, h->d_obs, h->d_values, h->d_state,
                       h->d_residuals, h->d_gradient, h->d_tile_partial, h->d_fail, h->d_scalars, h->d_partial,
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
@@ -2052,6 +2040,12 @@ int b200_evaluate(b200_handle* h, const double* state, double* cost, double* res
     h->residuals_resident = true;  // the copy in HBM stays valid until the next evaluation that asks for residuals
   }
   if (gradient != nullptr) OK(down_params(h, gradient, h->d_gradient));
+  return B200_OK;
+}
+
+int b200_set_apply_loss_function(b200_handle* h, int apply) {
+  if (h == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null handle");
+  h->apply_loss = apply != 0;
   return B200_OK;
 }
 

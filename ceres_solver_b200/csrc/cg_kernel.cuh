@@ -26,6 +26,38 @@ constexpr int kCgThreads = 256;
 
 enum CgMode { CG_NORMAL = 0, CG_RESET_FIRST = 1, CG_RESET_SECOND = 2, CG_BEGIN = 3 };
 
+constexpr int kMaxXchgRanks = 8;
+struct XchgPeers {
+  uint4* buf[kMaxXchgRanks];   // every rank's exchange buffer [2 slots][world][9C] packets, as mapped into THIS process
+  int world, rank;
+};
+
+__device__ __forceinline__ void xchg_store(uint4* dst, double v, unsigned epoch) {
+  const unsigned lo = static_cast<unsigned>(__double2loint(v)), hi = static_cast<unsigned>(__double2hiint(v));
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(epoch), "r"(hi), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ double xchg_wait_load(const uint4* src, unsigned epoch) {
+  unsigned a, b, c, d;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(src) : "memory");
+    if (b == epoch && d == epoch) break;
+    if (clock64() - t0 > 8000000000LL) __trap();   // a peer that never arrives must not hang this GPU
+  }
+  return __hiloint2double(static_cast<int>(c), static_cast<int>(a));
+}
+// this rank's partial v of entry j -> every peer; returns the rank-ordered sum over all ranks' partials of entry j
+__device__ __forceinline__ double xchg_allsum(const XchgPeers& xg, int slot, unsigned epoch, int n, int j, double v) {
+  const size_t base = static_cast<size_t>(slot) * xg.world * n;
+#pragma unroll
+  for (int p = 0; p < kMaxXchgRanks; ++p)
+    if (p < xg.world && p != xg.rank) xchg_store(xg.buf[p] + base + static_cast<size_t>(xg.rank) * n + j, v, epoch);
+  double acc = 0.0;
+  for (int r = 0; r < xg.world; ++r)
+    acc += (r == xg.rank) ? v : xchg_wait_load(xg.buf[xg.rank] + base + static_cast<size_t>(r) * n + j, epoch);
+  return acc;
+}
+
 struct CgVecArgs {
   CgParams prm;
   int mode;
@@ -46,21 +78,21 @@ struct CgVecArgs {
   int num_pq_parts;
   double* seed_pq;
   // Multi-GPU (observations sharded, cameras replicated): q = S p is the sum over ranks of the ranks' partial products.
-  // Every rank's push kernel has stored its partial into slot [xg_slot][rank] of EVERY rank's exchange buffer over NVLink
-  // and then raised flag [xg_slot][rank] to xg_epoch; this kernel waits for the `xg_world` flags and sums the partials in
-  // rank order -- the same order on every rank, so the replicated PCG state stays bit-identical without a collective.
-  const double* xg_buf;        // null: single GPU / q already complete
-  const unsigned* xg_flags;
-  int xg_world, xg_slot;
+  // The exchange happens INSIDE this kernel, NCCL-LL style: every thread packs its entries of this rank's partial (a.q)
+  // into 16-byte packets {lo32, epoch, hi32, epoch} and stores them straight into every peer's exchange buffer
+  // (peer-mapped pointers, NVLink), then polls its own buffer until the packets of all ranks carry the current epoch and
+  // sums the partials in RANK ORDER -- the same order on every rank, so the replicated PCG state stays bit-identical.
+  // No fences, no flags kernel, no collective: one NVLink write latency on top of the vector update.
+  XchgPeers xg;                // xg.world == 0: single GPU / q already complete
+  int xg_slot;
   unsigned xg_epoch;
   unsigned* bar;               // {arrival count, generation}: grid barrier of an ORDINARY launch (all CTAs co-resident: the
                                // grid is at most one CTA per SM and the stream holds nothing else while it runs); null: the
                                // kernel was launched cooperatively and uses cooperative-groups grid.sync()
 };
 
-// Reusable grid-wide barrier for a grid whose CTAs are all resident.  ncu on the cooperative launch of this kernel showed
-// 20 k cycles elapsed for 5.4 k active (profiles/r02_cg_vector_ncu.txt): the cooperative launch path itself costs more
-// than the kernel's work, so the kernel is launched normally and synchronises through two words in global memory.
+// Reusable grid-wide barrier for a grid whose CTAs are all resident (development A/B only: measured 3 % SLOWER per CG
+// iteration than the cooperative launch + grid.sync() it was meant to replace, so the product keeps the cooperative launch).
 // A wait that lasts longer than ~2 s traps (a barrier that can never complete must not hang the GPU).
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
   __syncthreads();
@@ -167,7 +199,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     bj = a.rhs[j0];
     if (mode != CG_BEGIN) {
       pj = a.p[j0];
-      if (a.xg_buf == nullptr) qj = a.q[j0];
+      if (a.xg.world <= 1) qj = a.q[j0];
       xj = a.x[j0];
       if (mode != CG_RESET_SECOND) rj = a.r[j0];
     }
@@ -181,33 +213,17 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   }
 
   if (mode != CG_BEGIN && st_done) return;
-  if (a.xg_buf != nullptr && mode != CG_BEGIN) {
-    // gather: wait for every rank's partial of q, then sum them in rank order (replaces qj / a.q)
-    if (tid < a.xg_world) {
-      const volatile unsigned* fl = a.xg_flags + a.xg_slot * a.xg_world + tid;
-      const long long t0 = clock64();
-      while (*fl != a.xg_epoch) {
-        if (clock64() - t0 > 8000000000LL) __trap();   // a peer that never arrives must not hang this GPU
-      }
-      __threadfence_system();
-    }
-    __syncthreads();
-    const double* part = a.xg_buf + static_cast<size_t>(a.xg_slot) * a.xg_world * n;
+  if (a.xg.world > 1 && mode != CG_BEGIN) {
+    // exchange + rank-ordered sum of the partial products (replaces qj / a.q)
     if (single) {
       if (ok0) {
-        double acc = 0.0;
-        for (int r = 0; r < a.xg_world; ++r) acc += __ldcg(part + static_cast<size_t>(r) * n + j0);
-        qj = acc;
-        a.q[j0] = acc;
+        qj = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n, j0, __ldcg(a.q + j0));
+        a.q[j0] = qj;
       }
     } else {
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int j = blk * kCgCamsPerCta * 9 + tid;
-        if (lane_ok && j < n) {
-          double acc = 0.0;
-          for (int r = 0; r < a.xg_world; ++r) acc += __ldcg(part + static_cast<size_t>(r) * n + j);
-          a.q[j] = acc;
-        }
+        if (lane_ok && j < n) a.q[j] = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n, j, __ldcg(a.q + j));
       }
     }
   }
@@ -453,40 +469,6 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     st->rho = rho_new;
     st->Q0 = Q0_next;
     st->iteration = it;
-  }
-}
-
-// Multi-GPU exchange, sender side: copies this rank's partial product (n doubles) into slot [slot][rank] of every rank's
-// exchange buffer (peer-mapped pointers: the stores travel over NVLink), then -- once every CTA's stores are fenced -- the
-// last CTA raises flag [slot][rank] to `epoch` on every rank.  No-op once the PCG has terminated.
-constexpr int kMaxXchgRanks = 8;
-struct XchgPeers {
-  double* buf[kMaxXchgRanks];
-  unsigned* flags[kMaxXchgRanks];
-  int world, rank;
-};
-__global__ void __launch_bounds__(256) xchg_push_kernel(XchgPeers xp, int n, int slot, unsigned epoch, const double* __restrict__ src,
-                                                        unsigned* counter, const int* __restrict__ done_flag) {
-  if (done_flag != nullptr && __ldcg(done_flag) != 0) return;
-  const size_t base = (static_cast<size_t>(slot) * xp.world + xp.rank) * n;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const double v = __ldcg(src + i);
-#pragma unroll
-    for (int p = 0; p < kMaxXchgRanks; ++p)
-      if (p < xp.world) xp.buf[p][base + i] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (atomicAdd(counter, 1u) == gridDim.x - 1u) {
-      atomicExch(counter, 0u);
-      __threadfence_system();
-      for (int p = 0; p < xp.world; ++p) {
-        volatile unsigned* f = xp.flags[p] + slot * xp.world + xp.rank;
-        *f = epoch;
-      }
-      __threadfence_system();
-    }
   }
 }
 

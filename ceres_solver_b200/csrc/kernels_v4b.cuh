@@ -47,8 +47,122 @@ __device__ __forceinline__ void seg_suffix_sum(double (&w)[K], int seg_end, int 
   }
 }
 
+// The 33..kTile-row points of the CTA for the implicit-Schur initialisation (staging as in schur_mul_big_points_impl): the
+// nine sums of E'E and E'b go through a CTA reduction, every row then finishes like a warp-tile row; the camera part is
+// added to replica 0 of the private camera vector with shared-memory atomics.
+__device__ __forceinline__ void init_big_points_impl(const V2View& v, const BigStage& st, uint32_t& parity, double* sy_rep0, int2 cr,
+                                                     const InitV4Args& a) {
+  const int2 br = v.cta_big[blockIdx.x];
+  const int tid = threadIdx.x;
+  double* sU = st.sU;
+  for (int b = br.x; b < br.y; ++b) {
+    const TileDesc d = v.big_tiles[b];
+    if (tid == 0) {
+      mbar_arrive_expect_tx(st.bar, d.obs_count * 192u);
+      for (int r0 = 0, k = 0; r0 < d.obs_count; r0 += st.chunk_rows, ++k) {
+        const int rows = min(st.chunk_rows, d.obs_count - r0);
+        unsigned char* dst = st.base + static_cast<size_t>(k) * st.chunk_stride;
+        bulk_g2s(dst, v.p.F() + 18 * static_cast<size_t>(d.obs_begin + r0), rows * 144u, st.bar);
+        bulk_g2s(dst + st.chunk_rows * 144, v.p.E() + 6 * static_cast<size_t>(d.obs_begin + r0), rows * 48u, st.bar);
+      }
+    }
+    const bool active = tid < d.obs_count;
+    const int chunk = tid / st.chunk_rows, rr = tid - chunk * st.chunk_rows;
+    const double* sF = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride) + rr * 18;
+    const double* sE = reinterpret_cast<const double*>(st.base + static_cast<size_t>(chunk) * st.chunk_stride + st.chunk_rows * 144) + rr * 6;
+    const size_t row = static_cast<size_t>(d.obs_begin) + tid;
+    const size_t pt = static_cast<size_t>(d.pt_begin);
+    int cam_l = 0;
+    double2 bb = make_double2(0, 0);
+    if (active) {
+      cam_l = meta_local(v, __ldg(v.row_meta + row), cr);
+      bb = *reinterpret_cast<const double2*>(a.b + 2 * row);
+    }
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    if (a.D != nullptr) {
+      d0 = __ldg(a.D + 3 * pt);
+      d1 = __ldg(a.D + 3 * pt + 1);
+      d2 = __ldg(a.D + 3 * pt + 2);
+    }
+    mbar_wait(st.bar, parity);
+    parity ^= 1;
+    double f[18];
+    double2 e0 = make_double2(0, 0), e1 = e0, e2 = e0;
+    double m[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 w = lds2(sF + 2 * k);
+        f[2 * k] = w.x;
+        f[2 * k + 1] = w.y;
+      }
+      e0 = lds2(sE);
+      e1 = lds2(sE + 2);
+      e2 = lds2(sE + 4);
+      m[0] = e0.x * e0.x + e1.y * e1.y;
+      m[1] = e0.x * e0.y + e1.y * e2.x;
+      m[2] = e0.x * e1.x + e1.y * e2.y;
+      m[3] = e0.y * e0.y + e2.x * e2.x;
+      m[4] = e0.y * e1.x + e2.x * e2.y;
+      m[5] = e1.x * e1.x + e2.y * e2.y;
+      m[6] = e0.x * bb.x + e1.y * bb.y;
+      m[7] = e0.y * bb.x + e2.x * bb.y;
+      m[8] = e1.x * bb.x + e2.y * bb.y;
+    }
+    if (tid < kTile) {  // the first four warps hold all rows
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m[k] += __shfl_xor_sync(0xffffffffu, m[k], o);
+      }
+      if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) sU[(tid >> 5) * 9 + k] = m[k];
+      }
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) m[k] = (sU[k] + sU[9 + k]) + (sU[18 + k] + sU[27 + k]);
+      m[0] += d0 * d0;
+      m[3] += d1 * d1;
+      m[5] += d2 * d2;
+      double inv[6];
+      invert_sym3_llt(m, inv);
+      const double v0 = inv[0] * m[6] + inv[1] * m[7] + inv[2] * m[8];
+      const double v1 = inv[1] * m[6] + inv[3] * m[7] + inv[4] * m[8];
+      const double v2 = inv[2] * m[6] + inv[4] * m[7] + inv[5] * m[8];
+      if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.ete_inv[6 * pt + k] = inv[k];
+        if (a.ye != nullptr) {
+          a.ye[3 * pt] = v0;
+          a.ye[3 * pt + 1] = v1;
+          a.ye[3 * pt + 2] = v2;
+        }
+      }
+      const double t0 = bb.x - (e0.x * v0 + e0.y * v1 + e1.x * v2);
+      const double t1 = bb.y - (e1.y * v0 + e2.x * v1 + e2.y * v2);
+      double* yc = sy_rep0 + 9 * cam_l;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(yc + k, f[k] * t0 + f[9 + k] * t1);
+      if (a.q3 != nullptr) {
+        const double pa = inv[0] * e0.x + inv[1] * e0.y + inv[2] * e1.x, pb = inv[1] * e0.x + inv[3] * e0.y + inv[4] * e1.x,
+                     pc = inv[2] * e0.x + inv[4] * e0.y + inv[5] * e1.x;
+        const double pd = inv[0] * e1.y + inv[1] * e2.x + inv[2] * e2.y, pe = inv[1] * e1.y + inv[3] * e2.x + inv[4] * e2.y,
+                     pf = inv[2] * e1.y + inv[4] * e2.x + inv[5] * e2.y;
+        double* q = a.q3 + 3 * row;
+        q[0] = 1.0 - (e0.x * pa + e0.y * pb + e1.x * pc);
+        q[1] = -(e1.y * pa + e2.x * pb + e2.y * pc);
+        q[2] = 1.0 - (e1.y * pd + e2.x * pe + e2.y * pf);
+      }
+    }
+    __syncthreads();  // staging and sU are reused by the next point
+  }
+}
+
 // ete_inv[k] = (sum_rows E'E + D_k^2)^-1 ; ye = ete_inv E'b ; rhs += F'(b - E ye) ; q3[r] = I - E_r ete_inv E_r'
-// Warp tiles only (points with <= 32 rows); the 33+-row points go through schur_init_kernel / huge_schur_init_kernel and
+// Warp tiles and the CTA's 33..kTile-row points; the slices of larger points go through huge_schur_init_kernel and
 // row_q_tiles_kernel.
 template <bool kOwned>
 __global__ void __launch_bounds__(kV4MaxThreads, 1) schur_init_v4_kernel(V2View v, InitV4Args a) {
@@ -169,6 +283,21 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1) schur_init_v4_kernel(V2View 
     if (kOwned) cam_accumulate9_owned(my_y, cam_l, active, g);
     else cam_accumulate9(my_y, cam_l, active, g);
   }
+  {  // the CTA's 33..kTile-row points (uniform per CTA), processed by the whole CTA
+    const int2 br = v.cta_big[blockIdx.x];
+    if (br.y > br.x) {
+      double* sw0 = reinterpret_cast<double*>(c.ring() + v.stages * kV4StageBytes);
+      BigStage st;
+      st.base = c.ring();
+      st.chunk_rows = kV4BigChunkRows;
+      st.chunk_stride = v.per_warp_bytes;
+      st.sU = sw0 + 48;   // 4 warps x 9 partial sums
+      st.bar = reinterpret_cast<uint64_t*>(c.ring() + v4_extra_offset(v.stages));
+      __syncthreads();  // every warp is done with its ring slot
+      uint32_t parity = 0;
+      init_big_points_impl(v, st, parity, c.sy(), cr, a);
+    }
+  }
   v2_epilogue(v, c.sy(), cr, a.rhs);
 }
 
@@ -198,44 +327,96 @@ __global__ void __launch_bounds__(kTile) row_q_tiles_kernel(ProblemView p, const
 // flight than one 8-warp CTA did); the 45 packed entries are reduced across the lanes by recursive halving (each lane ends with <= 2 entries: 46 64-bit exchanges
 // instead of 225) and added with <= 2 REDs per lane.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+constexpr int kCamBlkRowBytes = 144 + 24;                 // F row + Q block
+constexpr int kCamBlkWarpBytes = 2 * 32 * kCamBlkRowBytes;  // two buffers of 32 rows per warp
+constexpr int kCamBlkThreads = 128;
+
+// Each lane copies ITS row of the warp's next 32 (gathered) rows into the warp's shared-memory buffer with cp.async while
+// the warp computes on the previous 32: the gathers stay in flight during the arithmetic, so the kernel is no longer bound by
+// the round-trip latency of dependent loads at 12 resident warps (ncu on the register version: 43 % long-scoreboard stalls).
 template <bool kSchur>
-__global__ void __launch_bounds__(128, 3)
+__global__ void __launch_bounds__(kCamBlkThreads, 3)
     cam_blocks_v2_kernel(ProblemView p, int num_items, const CamItem* __restrict__ items, const int* __restrict__ cam_rows,
                          const double* __restrict__ q3, double* out45) {
+  extern __shared__ __align__(128) unsigned char cb_smem[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  unsigned char* wbuf = cb_smem + (threadIdx.x >> 5) * kCamBlkWarpBytes;
   for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < num_items; item += gridDim.x * warps_per_block) {
     const CamItem it = items[item];
     double m[46];
 #pragma unroll
     for (int k = 0; k < 46; ++k) m[k] = 0.0;
-    for (int j = it.begin + lane; j < it.end; j += 32) {
-      const int r = __ldg(cam_rows + j);
-      const double2* fp = reinterpret_cast<const double2*>(p.F() + 18 * static_cast<size_t>(r));
-      double f[18];
+    const int iters = (it.end - it.begin + 31) >> 5;
+    auto row_of = [&](int iter) -> int {
+      const int j = it.begin + 32 * iter + lane;
+      return (iter < iters && j < it.end) ? __ldg(cam_rows + j) : -1;
+    };
+    auto issue = [&](int r, int buf) {
+      if (r >= 0) {
+        unsigned char* dst = wbuf + buf * 32 * kCamBlkRowBytes + lane * 144;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.F() + 18 * static_cast<size_t>(r));
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double2 w = __ldg(fp + k);
-        f[2 * k] = w.x;
-        f[2 * k + 1] = w.y;
-      }
-      double q00 = 1.0, q01 = 0.0, q11 = 1.0;
-      if (kSchur) {
-        q00 = __ldg(q3 + 3 * static_cast<size_t>(r));
-        q01 = __ldg(q3 + 3 * static_cast<size_t>(r) + 1);
-        q11 = __ldg(q3 + 3 * static_cast<size_t>(r) + 2);
-      }
-      int idx = 0;
-#pragma unroll
-      for (int aa = 0; aa < 9; ++aa) {
-        const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
-#pragma unroll
-        for (int bb = aa; bb < 9; ++bb) {
-          m[idx] += ga * f[bb] + gb * f[9 + bb];
-          ++idx;
+        for (int k = 0; k < 9; ++k) cp_async16(dst + 16 * k, src + 16 * k);
+        if (kSchur) {
+          unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24;
+          const double* sq = q3 + 3 * static_cast<size_t>(r);
+          cp_async8(dq, sq);
+          cp_async8(dq + 8, sq + 1);
+          cp_async8(dq + 16, sq + 2);
         }
       }
+      cp_async_commit();
+    };
+    int r_cur = row_of(0), r_nxt = row_of(1);
+    issue(r_cur, 0);
+    for (int i = 0; i < iters; ++i) {
+      const int r_nn = row_of(i + 2);
+      issue(r_nxt, (i + 1) & 1);
+      cp_async_wait<1>();
+      __syncwarp();
+      if (r_cur >= 0) {
+        const double* fr = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + lane * 144);
+        double f[18];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double2 w = lds2(fr + 2 * k);
+          f[2 * k] = w.x;
+          f[2 * k + 1] = w.y;
+        }
+        double q00 = 1.0, q01 = 0.0, q11 = 1.0;
+        if (kSchur) {
+          const double* q = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24);
+          q00 = q[0];
+          q01 = q[1];
+          q11 = q[2];
+        }
+        int idx = 0;
+#pragma unroll
+        for (int aa = 0; aa < 9; ++aa) {
+          const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
+#pragma unroll
+          for (int bb = aa; bb < 9; ++bb) {
+            m[idx] += ga * f[bb] + gb * f[9 + bb];
+            ++idx;
+          }
+        }
+      }
+      __syncwarp();   // the buffer is refilled two iterations later
+      r_cur = r_nxt;
+      r_nxt = r_nn;
     }
+    cp_async_wait<0>();
     // recursive halving over the lanes: 46 -> 23 -> 12 -> 6 -> 3 -> 2 entries per lane (zero padded)
     int base = 0;
     double r1[23], r2[12], r3[6], r4[3], r5[2];

@@ -88,6 +88,9 @@ int64_t b200_num_residuals(const b200_handle* h);  /* Evaluator::NumResiduals   
  * gradient = J'r of the unscaled Jacobian.  Returns B200_ERR_EVALUATION_FAILED where Evaluate returns false. */
 int b200_evaluate(b200_handle* h, const double* state, double* cost, double* residuals, double* gradient,
                   int want_jacobian);
+/* Evaluator::EvaluateOptions::apply_loss_function (evaluator.h:101-102): apply == 0 makes the following evaluations
+ * skip the robust correction (rho, Corrector) of the loss given at b200_create; apply != 0 (the default) restores it. */
+int b200_set_apply_loss_function(b200_handle* h, int apply);
 /* Evaluator::Plus (evaluator.h:146; Euclidean manifolds only): x_plus_delta = x + delta. */
 int b200_plus(b200_handle* h, const double* x, const double* delta, double* x_plus_delta);
 
