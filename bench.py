@@ -155,6 +155,68 @@ def run_reference(args, bal, desc, rank0=True):
     return {"value": iters / dt, "seconds": dt, "iterations": iters, "cores": nt, "trace": recs, "times": times}
 
 
+def run_spmv_sweep(args):
+    """BASELINE.json configs[4] / SURVEY 8d I4: synthetic block-SpMV sweep, N residual blocks of shape (2x3 + 2x9), P = N/4
+    points, C = max(16, N/400) cameras, rows point-sorted, cameras uniform random, values and x ~ N(0,1) from MT19937 with
+    its default seed (the set-up of the reference's own spmv_benchmark.cc:70-80 / evaluation_benchmark.cc:147-153).  Per size:
+    the 2x3-only products (E x, E'y), the 2x9-only ones (F x, F'y), both shapes (J x, J'y) and (J'J + D^2) x in one pass, as
+    GB/s of algorithmic bytes over CUDA-event kernel time and as a fraction of the measured HBM peak."""
+    import torch
+    import ceres_solver_b200 as cs
+    peak, peak_src = load_peaks()
+    sizes = [int(float(v)) for v in (args.sizes.split(",") if args.sizes else ["1e5", "3e5", "1e6", "3e6", "1e7", "3e7"])]
+    rows = []
+    names = {"pmv_right_e": "E x (2x3)", "pmv_left_e": "E'y (2x3)", "pmv_right_f": "F x (2x9)", "pmv_left_f": "F'y (2x9)",
+             "jacobian_multiply": "J x (both)", "jacobian_t_multiply": "J'y (both)", "jtj_multiply": "(J'J + D^2) x"}
+    for N in sizes:
+        N -= N % 4
+        P, C = N // 4, max(16, N // 400)
+        rng = np.random.RandomState(5489)
+        pt = np.repeat(np.arange(P, dtype=np.int32), 4)
+        base = rng.randint(0, C, P).astype(np.int64)
+        step = rng.randint(1, max(2, C // 4), P).astype(np.int64)
+        cam = ((base[:, None] + step[:, None] * np.arange(4)[None, :]) % C).astype(np.int32).ravel()   # 4 distinct cameras
+        gpu = cs.Problem(C, P, cam, pt, np.zeros(2 * N))
+        vals = rng.standard_normal(24 * N)
+        gpu.set_jacobian_values(vals)
+        del vals
+        x = rng.standard_normal(gpu.num_parameters)
+        D = np.abs(rng.standard_normal(gpu.num_parameters)) + 0.1
+        y = rng.standard_normal(gpu.num_residuals)
+        reps = 5 if N <= 3_000_000 else 2
+
+        def ops():
+            gpu.partitioned_multiply(0, x[:3 * P])
+            gpu.partitioned_multiply(2, y)
+            gpu.partitioned_multiply(1, x[3 * P:])
+            gpu.partitioned_multiply(3, y)
+            gpu.right_multiply(x)
+            gpu.left_multiply(y)
+            gpu.jtj_multiply(x, D)
+        ops()   # warm-up
+        gpu.stats_reset()
+        gpu.profile(True)
+        for _ in range(reps):
+            ops()
+        st = gpu.stats()
+        gpu.profile(False)
+        row = {"N": N, "P": P, "C": C, "jacobian_bytes": 192 * N, "ops": {}}
+        for k, label in names.items():
+            r = op_rate(st.get(k), peak)
+            if r:
+                row["ops"][label] = {"GBps": r["GBps"], "frac": r["frac"], "mean_op_ms": r["mean_op_ms"]}
+        rows.append(row)
+        gpu.close()
+        torch.cuda.empty_cache()
+    last = rows[-1]["ops"].get("(J'J + D^2) x", {})
+    line = {"metric": "block_spmv_GBps", "value": last.get("GBps"), "unit": "GB/s", "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": "spmv-sweep: N residual blocks (2x3 + 2x9), P = N/4, "
+            "C = max(16, N/400), point-sorted rows, uniform random cameras, values ~ N(0,1) MT19937(5489)"},
+            "peak": peak, "peak_source": peak_src, "sweep": rows}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +225,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sizes", default=None, help="spmv-sweep: comma separated N list (default 1e5..3e7; 1e8 needs ~60 GB host RAM)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -170,6 +233,8 @@ def main():
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line (NCCL prints its version banner there)
     workload = args.workload or "ladybug-1723"
+    if workload == "spmv-sweep":
+        return run_spmv_sweep(args) if rank == 0 and args.impl == "b200" else 0
 
     if args.impl == "reference":
         if rank != 0:

@@ -77,7 +77,7 @@ SYMBOLS = [
     "b200_nccl_unique_id", "b200_create", "b200_destroy", "b200_last_error", "b200_num_parameters",
     "b200_num_residuals", "b200_evaluate", "b200_set_apply_loss_function", "b200_plus", "b200_jacobian_squared_column_norm",
     "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply", "b200_model_cost_change",
-    "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_jtj_multiply", "b200_solver_options_default",
+    "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_partitioned_multiply", "b200_jtj_multiply", "b200_solver_options_default",
     "b200_schur_solve", "b200_dense_schur_solve", "b200_schur_init", "b200_schur_rhs", "b200_schur_ete_inverse", "b200_schur_multiply",
     "b200_schur_back_substitute", "b200_schur_jacobi_update", "b200_block_jacobi_update",
     "b200_lm_options_default", "b200_lm_solve", "b200_profile_enable", "b200_stats_reset", "b200_stats_get",
@@ -195,6 +195,13 @@ class Problem:
     def left_multiply(self, x, y=None):
         y = np.zeros(self.num_parameters) if y is None else _f64(y).copy()
         _check(lib().b200_jacobian_left_multiply(self.h, _d(_f64(x)), _d(y)))
+        return y
+
+    def partitioned_multiply(self, op, x, y=None):
+        """op: 0 y += E x_e, 1 y += F x_f, 2 y += E'x, 3 y += F'x  (PartitionedMatrixView)."""
+        n_out = (self.num_residuals, self.num_residuals, 3 * self.P, 9 * self.C)[op]
+        y = np.zeros(n_out) if y is None else _f64(y).copy()
+        _check(lib().b200_partitioned_multiply(self.h, int(op), _d(_f64(x)), _d(y)))
         return y
 
     def jtj_multiply(self, x, D=None):

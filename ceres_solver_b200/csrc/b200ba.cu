@@ -30,6 +30,7 @@
 #include "kernels_v2.cuh"
 #include "kernels_v2b.cuh"
 #include "kernels_v4b.cuh"
+#include "pmv_kernels.cuh"
 #include "vector_kernels.cuh"
 #include "cg_kernel.cuh"
 #include "spse_kernels.cuh"
@@ -41,6 +42,7 @@ using namespace b200;
 namespace {
 
 thread_local std::string g_error;
+constexpr int kHostThreads = 8;   // host-side vector passes of the host-boundary LM loop (the reference uses its thread pool)
 
 // Development switches (A/B measurements of kernel variants and tuning knobs) exist only in builds with
 // -DB200_DEV_KNOBS; the product library has a single code path per problem class and reads no such variable.
@@ -90,13 +92,17 @@ enum KernelId {
   K_MODEL_COST,
   K_CG_VEC,
   K_LM_VEC,
+  K_PMV_RIGHT_E,
+  K_PMV_RIGHT_F,
+  K_PMV_LEFT_E,
+  K_PMV_LEFT_F,
   K_MISC,
   K_COUNT
 };
 const char* kKernelNames[K_COUNT] = {"evaluate_jacobian", "evaluate_cost", "squared_column_norm", "scale_columns",
                                      "jacobian_multiply", "jacobian_t_multiply", "jtj_multiply", "schur_init",
                                      "schur_multiply", "schur_multiply_big_points", "camera_reduce", "schur_diag_blocks", "invert_9x9", "back_substitute",
-                                     "model_cost", "cg_vector", "lm_vector", "misc"};
+                                     "model_cost", "cg_vector", "lm_vector", "pmv_right_e", "pmv_right_f", "pmv_left_e", "pmv_left_f", "misc"};
 
 // cuSOLVER (dense Cholesky of the explicit reduced camera system) is bound lazily with dlopen like NCCL: the
 // library is only touched by b200_dense_schur_solve, and shares whatever libcusolver.so.11 the process already has.
@@ -566,7 +572,7 @@ int schur_init_dev(b200_handle* h, const double* d_b, const double* d_D) {
     ia.D = d_D;
     ia.ete_inv = h->d_ete_inv;
     ia.rhs = h->d_rhs;
-    ia.ye = h->d_ye;
+    ia.ye = nullptr;   // (E'E)^-1 E'b is not consumed by anything on this path: not written
     ia.q3 = h->cam_major_ok ? h->d_q3 : nullptr;
     OK(launch(h, K_SCHUR_INIT, [&] {
       V2View iv = h->v2_mul;
@@ -1498,7 +1504,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         max_range = std::max(max_range, hi - lo);
       }
       // <= ~4 us of REDs at the measured 95 G lane-RED/s; list positions must fit the row word
-      long direct_limit = 400000;
+      long direct_limit = 700000;   // REDs of the flush: <= ~7 us at the measured 95 G lane-RED/s, still far cheaper than partial vectors
       if (const char* e = dev_env("B200_DIRECT_LIMIT")) direct_limit = atol(e);
       direct_mode = 9 * list_total <= direct_limit && max_list <= static_cast<int>(kMetaLocalMask) && C <= static_cast<int>(kMetaCamMask);
       if (C > static_cast<int>(kMetaCamMask)) v2_possible = false;   // camera ids do not fit the row word: CTA-tile kernels
@@ -1979,6 +1985,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   h->bytes_per_op[K_SCALE] = 2 * 192 * Nn + 8 * Nn + 8.0 * (3 * Pp + 9 * Cc);
   h->bytes_per_op[K_JMUL] = 196 * Nn + 32 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
   h->bytes_per_op[K_JTMUL] = 196 * Nn + 16 * Nn + 4 * Pp + 16.0 * (3 * Pp + 9 * Cc);
+  h->bytes_per_op[K_PMV_RIGHT_E] = 48 * Nn + 4 * Nn + 32 * Nn + 24 * Pp;            // E cells, point id, y read + written, x_e
+  h->bytes_per_op[K_PMV_RIGHT_F] = 144 * Nn + 4 * Nn + 32 * Nn + 72 * Cc;           // F cells, camera id, y read + written, x_f
+  h->bytes_per_op[K_PMV_LEFT_E] = 48 * Nn + 16 * Nn + 4 * Pp + 48 * Pp;             // E cells, y, chunk boundaries, x_e read + written
+  h->bytes_per_op[K_PMV_LEFT_F] = 144 * Nn + 16 * Nn + 4 * Nn + 144 * Cc;           // F cells, y, row list, x_f read + written
   h->bytes_per_op[K_MODEL_COST] = 196 * Nn + 16 * Nn + 4 * Pp + 8.0 * (3 * Pp + 9 * Cc);
   return B200_OK;
 }
@@ -2114,6 +2124,55 @@ int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y) {
   }));
   OK(allreduce_sum(h, h->d_vp0 + 3 * static_cast<size_t>(h->P), 9 * static_cast<size_t>(h->C)));
   return down_params(h, y, h->d_vp0);
+}
+
+int b200_partitioned_multiply(b200_handle* h, int op, const double* x, double* y) {
+  if (h == nullptr || x == nullptr || y == nullptr) return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  if (op < B200_PMV_RIGHT_E || op > B200_PMV_LEFT_F) return fail(B200_ERR_INVALID_ARGUMENT, "unknown partitioned product %d", op);
+  if (h->world > 1) return fail(B200_ERR_UNSUPPORTED, "partitioned products are single-GPU");
+  CU(cudaSetDevice(h->device));
+  const size_t nE = 3 * static_cast<size_t>(h->P), nF = 9 * static_cast<size_t>(h->C);
+  double* d_par = h->d_vp0;   // [points | cameras] scratch
+  double* d_row = h->d_vr0;   // [2N] scratch
+  // point-sized vectors cross the boundary in the caller's point order, row-sized ones in its row order
+  auto up_e = [&](const double* host) -> int {
+    if (!h->permuted) return h2d(h, d_par, host, sizeof(double) * nE);
+    OK(h2d(h, h->d_stage_p, host, sizeof(double) * nE));
+    return permute_blocks(h, true, h->P, 3, h->d_pt_perm, h->d_stage_p, d_par);
+  };
+  auto down_e = [&](double* host) -> int {
+    if (!h->permuted) return d2h(h, host, d_par, sizeof(double) * nE);
+    OK(permute_blocks(h, false, h->P, 3, h->d_pt_perm, d_par, h->d_stage_p));
+    return d2h(h, host, h->d_stage_p, sizeof(double) * nE);
+  };
+  switch (op) {
+    case B200_PMV_RIGHT_E:
+      OK(up_e(x));
+      OK(up_rows(h, d_row, y));
+      OK(launch(h, K_PMV_RIGHT_E, [&] { pmv_right_e_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, d_par, d_row); }));
+      return down_rows(h, y, d_row);
+    case B200_PMV_RIGHT_F:
+      OK(h2d(h, d_par + nE, x, sizeof(double) * nF));
+      OK(up_rows(h, d_row, y));
+      OK(launch(h, K_PMV_RIGHT_F, [&] { pmv_right_f_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, d_par + nE, d_row); }));
+      return down_rows(h, y, d_row);
+    case B200_PMV_LEFT_E:
+      OK(up_rows(h, d_row, x));
+      OK(up_e(y));
+      OK(launch(h, K_PMV_LEFT_E, [&] { pmv_left_e_kernel<<<flat_grid(h, h->P, 256), 256, 0, h->stream>>>(h->view, d_row, d_par); }));
+      return down_e(y);
+    default:
+      OK(up_rows(h, d_row, x));
+      OK(h2d(h, d_par + nE, y, sizeof(double) * nF));
+      if (h->cam_major_ok)
+        OK(launch(h, K_PMV_LEFT_F, [&] {
+          pmv_left_f_kernel<<<std::max(1, std::min((h->num_cam_items + 7) / 8, h->sm_count * 8)), 256, 0, h->stream>>>(
+              h->view, h->num_cam_items, h->d_cam_items, h->d_cam_rows, d_row, d_par + nE);
+        }));
+      else
+        OK(launch(h, K_PMV_LEFT_F, [&] { pmv_left_f_rows_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, d_row, d_par + nE); }));
+      return d2h(h, y, d_par + nE, sizeof(double) * nF);
+  }
 }
 
 int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* y) {
@@ -2359,14 +2418,18 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
       if (opt->jacobi_scaling) {
         if (iteration == 0) {
           OK(b200_jacobian_squared_column_norm(h, scaling.data()));
-          for (int i = 0; i < np; ++i) scaling[i] = 1.0 / (1.0 + std::sqrt(scaling[i]));
+          double* sc = scaling.data();
+#pragma omp parallel for num_threads(kHostThreads) schedule(static)
+          for (int i = 0; i < np; ++i) sc[i] = 1.0 / (1.0 + std::sqrt(sc[i]));
         }
         OK(b200_jacobian_scale_columns(h, scaling.data()));
       }
       double mx = 0, sq = 0;
+      const double* gr = gradient.data();
+#pragma omp parallel for num_threads(kHostThreads) schedule(static) reduction(max : mx) reduction(+ : sq)
       for (int i = 0; i < np; ++i) {
-        mx = std::max(mx, std::fabs(gradient[i]));
-        sq += gradient[i] * gradient[i];
+        mx = std::max(mx, std::fabs(gr[i]));
+        sq += gr[i] * gr[i];
       }
       it.gradient_max_norm = mx;
       it.gradient_norm = std::sqrt(sq);
@@ -2433,27 +2496,37 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
       // fused so that each array is streamed once)
       if (!reuse_diagonal) {
         OK(b200_jacobian_squared_column_norm(h, diagonal.data()));
+        double *dg = diagonal.data(), *ld = lmD.data();
+        const double lo = opt->min_lm_diagonal, hi = opt->max_lm_diagonal;
+#pragma omp parallel for num_threads(kHostThreads) schedule(static)
         for (int i = 0; i < np; ++i) {
-          diagonal[i] = std::min(std::max(diagonal[i], opt->min_lm_diagonal), opt->max_lm_diagonal);
-          lmD[i] = std::sqrt(diagonal[i] / radius);
+          dg[i] = std::min(std::max(dg[i], lo), hi);
+          ld[i] = std::sqrt(dg[i] / radius);
         }
       } else {
-        for (int i = 0; i < np; ++i) lmD[i] = std::sqrt(diagonal[i] / radius);
+        const double* dg = diagonal.data();
+        double* ld = lmD.data();
+#pragma omp parallel for num_threads(kHostThreads) schedule(static)
+        for (int i = 0; i < np; ++i) ld[i] = std::sqrt(dg[i] / radius);
       }
-      std::fill(sol.begin(), sol.end(), std::numeric_limits<double>::quiet_NaN());  // levenberg_marquardt_strategy.cc:108
+      // (levenberg_marquardt_strategy.cc:108 pre-fills the step with NaN so that a solver that silently writes nothing is
+      //  caught; here the solve either fills sol or reports FAILURE / FATAL_ERROR, which the code below checks)
       if (opt->linear_solver_type == B200_DENSE_SCHUR) OK(b200_dense_schur_solve(h, nullptr, lmD.data(), sol.data(), &ls));
       else OK(b200_schur_solve(h, nullptr /* residuals of the last evaluate, still in HBM */, lmD.data(), &so, sol.data(), &ls));
       if (ls.termination_type != B200_LS_FAILURE && ls.termination_type != B200_LS_FATAL_ERROR) {
         // step = -sol, delta = step * scaling, candidate = x + delta (Evaluator::Plus on Euclidean blocks) and the two
         // norms the minimizer needs, in one pass
         double acc_x = 0.0, acc_s = 0.0, bad = 0.0;
+        const double *sl = sol.data(), *xx = x.data(), *sc = scaling.data();
+        double *stp = step.data(), *cd = cand.data();
+#pragma omp parallel for num_threads(kHostThreads) schedule(static) reduction(+ : acc_x, acc_s, bad)
         for (int i = 0; i < np; ++i) {
-          const double si = -sol[i];
-          step[i] = si;
-          const double ci = x[i] + si * scaling[i];
-          cand[i] = ci;
-          acc_x += x[i] * x[i];
-          acc_s += (x[i] - ci) * (x[i] - ci);
+          const double si = -sl[i];
+          stp[i] = si;
+          const double ci = xx[i] + si * sc[i];
+          cd[i] = ci;
+          acc_x += xx[i] * xx[i];
+          acc_s += (xx[i] - ci) * (xx[i] - ci);
           bad += (si - si);  // NaN/Inf - itself is NaN, finite - itself is 0
         }
         step_finite = (bad == 0.0);

@@ -338,12 +338,73 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 constexpr int kCamBlkRowBytes = 144 + 24;                 // F row + Q block
-constexpr int kCamBlkWarpBytes = 2 * 32 * kCamBlkRowBytes;  // two buffers of 32 rows per warp
+constexpr int kCamBlkDepth = 3;                           // buffers per warp: data of two steps in flight behind the one computed
+constexpr int kCamBlkWarpBytes = kCamBlkDepth * 32 * kCamBlkRowBytes;
 constexpr int kCamBlkThreads = 128;
 
-// Each lane copies ITS row of the warp's next 32 (gathered) rows into the warp's shared-memory buffer with cp.async while
-// the warp computes on the previous 32: the gathers stay in flight during the arithmetic, so the kernel is no longer bound by
-// the round-trip latency of dependent loads at 12 resident warps (ncu on the register version: 43 % long-scoreboard stalls).
+// Sum of the 46 (zero padded) per-lane entries over the lanes by recursive halving: 46 -> 23 -> 12 -> 6 -> 3 -> 2 entries per
+// lane (46 64-bit exchanges instead of 45 x 5), then <= 2 REDs per lane into the camera's packed block.
+__device__ __forceinline__ void cam_block_flush(double (&m)[46], double* dst) {
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  double r1[23], r2[12], r3[6], r4[3], r5[2];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int k = 0; k < 23; ++k) {
+      const double keep = up ? m[23 + k] : m[k], give = up ? m[k] : m[23 + k];
+      r1[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+    }
+    base += up ? 23 : 0;
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const double hi = (12 + k < 23) ? r1[(12 + k < 23) ? 12 + k : 0] : 0.0;
+      const double keep = up ? hi : r1[k], give = up ? r1[k] : hi;
+      r2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+    }
+    base += up ? 12 : 0;
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double keep = up ? r2[6 + k] : r2[k], give = up ? r2[k] : r2[6 + k];
+      r3[k] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+    }
+    base += up ? 6 : 0;
+  }
+  {
+    const bool up = (lane & 2) != 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double keep = up ? r3[3 + k] : r3[k], give = up ? r3[k] : r3[3 + k];
+      r4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+    }
+    base += up ? 3 : 0;
+  }
+  {
+    const bool up = (lane & 1) != 0;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double hi = (k == 0) ? r4[2] : 0.0;
+      const double keep = up ? hi : r4[k], give = up ? r4[k] : hi;
+      r5[k] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+    }
+    base += up ? 2 : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (r5[k] != 0.0) red_add(dst + base + k, r5[k]);   // padding entries are exactly zero and never reach an index >= 45
+}
+
+// Camera-major block diagonal.  One warp walks a strided sequence of items (slices of one camera's row list) as ONE
+// continuous stream of 32-row steps: each lane copies ITS (gathered) row of step s+2 into the warp's shared-memory ring with
+// cp.async while the warp computes step s, and the row indices of step s+3 are already being fetched -- no load latency is
+// exposed, neither inside an item nor between items (ncu on the register version: 43 % long-scoreboard stalls at 8-12
+// resident warps).  The 45 packed entries stay in registers per lane and are reduced across the lanes when an item ends.
 template <bool kSchur>
 __global__ void __launch_bounds__(kCamBlkThreads, 3)
     cam_blocks_v2_kernel(ProblemView p, int num_items, const CamItem* __restrict__ items, const int* __restrict__ cam_rows,
@@ -351,127 +412,110 @@ __global__ void __launch_bounds__(kCamBlkThreads, 3)
   extern __shared__ __align__(128) unsigned char cb_smem[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
+  const int stride = gridDim.x * warps_per_block;
   unsigned char* wbuf = cb_smem + (threadIdx.x >> 5) * kCamBlkWarpBytes;
-  for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < num_items; item += gridDim.x * warps_per_block) {
-    const CamItem it = items[item];
-    double m[46];
+  struct Cursor {
+    int item, iter, begin, end;
+  };
+  auto load_item = [&](Cursor& c) {
+    c.iter = 0;
+    if (c.item < num_items) {
+      const CamItem it = items[c.item];
+      c.begin = it.begin;
+      c.end = it.end;
+    } else {
+      c.begin = c.end = 0;
+    }
+  };
+  auto advance = [&](Cursor& c) {
+    ++c.iter;
+    if (c.begin + 32 * c.iter >= c.end) {
+      c.item += stride;
+      load_item(c);
+    }
+  };
+  auto row_of = [&](const Cursor& c) -> int {
+    const int j = c.begin + 32 * c.iter + lane;
+    return (c.item < num_items && j < c.end) ? __ldg(cam_rows + j) : -1;
+  };
+  auto issue = [&](int r, int buf) {
+    if (r >= 0) {
+      unsigned char* dst = wbuf + buf * 32 * kCamBlkRowBytes + lane * 144;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.F() + 18 * static_cast<size_t>(r));
 #pragma unroll
-    for (int k = 0; k < 46; ++k) m[k] = 0.0;
-    const int iters = (it.end - it.begin + 31) >> 5;
-    auto row_of = [&](int iter) -> int {
-      const int j = it.begin + 32 * iter + lane;
-      return (iter < iters && j < it.end) ? __ldg(cam_rows + j) : -1;
-    };
-    auto issue = [&](int r, int buf) {
-      if (r >= 0) {
-        unsigned char* dst = wbuf + buf * 32 * kCamBlkRowBytes + lane * 144;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(p.F() + 18 * static_cast<size_t>(r));
+      for (int k = 0; k < 9; ++k) cp_async16(dst + 16 * k, src + 16 * k);
+      if (kSchur) {
+        unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24;
+        const double* sq = q3 + 3 * static_cast<size_t>(r);
+        cp_async8(dq, sq);
+        cp_async8(dq + 8, sq + 1);
+        cp_async8(dq + 16, sq + 2);
+      }
+    }
+    cp_async_commit();
+  };
+  Cursor cp, ix;
+  cp.item = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  load_item(cp);
+  ix = cp;
+  int r_cur = row_of(ix);
+  advance(ix);
+  int r_nxt = row_of(ix);
+  advance(ix);
+  int r_pend = row_of(ix);
+  advance(ix);
+  issue(r_cur, 0);
+  issue(r_nxt, 1);
+  double m[46];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) cp_async16(dst + 16 * k, src + 16 * k);
-        if (kSchur) {
-          unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24;
-          const double* sq = q3 + 3 * static_cast<size_t>(r);
-          cp_async8(dq, sq);
-          cp_async8(dq + 8, sq + 1);
-          cp_async8(dq + 16, sq + 2);
+  for (int k = 0; k < 46; ++k) m[k] = 0.0;
+  int stage = 0;
+  while (cp.item < num_items) {
+    const int r_far = row_of(ix);   // row indices three steps ahead: their latency hides behind this step
+    advance(ix);
+    issue(r_pend, stage == 0 ? 2 : stage - 1);   // data two steps ahead
+    cp_async_wait<2>();
+    __syncwarp();
+    if (r_cur >= 0) {
+      const double* fr = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + lane * 144);
+      double f[18];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 w = lds2(fr + 2 * k);
+        f[2 * k] = w.x;
+        f[2 * k + 1] = w.y;
+      }
+      double q00 = 1.0, q01 = 0.0, q11 = 1.0;
+      if (kSchur) {
+        const double* q = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24);
+        q00 = q[0];
+        q01 = q[1];
+        q11 = q[2];
+      }
+      int idx = 0;
+#pragma unroll
+      for (int aa = 0; aa < 9; ++aa) {
+        const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
+#pragma unroll
+        for (int bb = aa; bb < 9; ++bb) {
+          m[idx] += ga * f[bb] + gb * f[9 + bb];
+          ++idx;
         }
       }
-      cp_async_commit();
-    };
-    int r_cur = row_of(0), r_nxt = row_of(1);
-    issue(r_cur, 0);
-    for (int i = 0; i < iters; ++i) {
-      const int r_nn = row_of(i + 2);
-      issue(r_nxt, (i + 1) & 1);
-      cp_async_wait<1>();
-      __syncwarp();
-      if (r_cur >= 0) {
-        const double* fr = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + lane * 144);
-        double f[18];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const double2 w = lds2(fr + 2 * k);
-          f[2 * k] = w.x;
-          f[2 * k + 1] = w.y;
-        }
-        double q00 = 1.0, q01 = 0.0, q11 = 1.0;
-        if (kSchur) {
-          const double* q = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24);
-          q00 = q[0];
-          q01 = q[1];
-          q11 = q[2];
-        }
-        int idx = 0;
-#pragma unroll
-        for (int aa = 0; aa < 9; ++aa) {
-          const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
-#pragma unroll
-          for (int bb = aa; bb < 9; ++bb) {
-            m[idx] += ga * f[bb] + gb * f[9 + bb];
-            ++idx;
-          }
-        }
-      }
-      __syncwarp();   // the buffer is refilled two iterations later
-      r_cur = r_nxt;
-      r_nxt = r_nn;
     }
-    cp_async_wait<0>();
-    // recursive halving over the lanes: 46 -> 23 -> 12 -> 6 -> 3 -> 2 entries per lane (zero padded)
-    int base = 0;
-    double r1[23], r2[12], r3[6], r4[3], r5[2];
-    {
-      const bool up = (lane & 16) != 0;
+    if (cp.begin + 32 * (cp.iter + 1) >= cp.end) {   // last step of the item (uniform over the warp)
+      cam_block_flush(m, out45 + 45 * static_cast<size_t>(items[cp.item].cam));
 #pragma unroll
-      for (int k = 0; k < 23; ++k) {
-        const double keep = up ? m[23 + k] : m[k], give = up ? m[k] : m[23 + k];
-        r1[k] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
-      }
-      base += up ? 23 : 0;
+      for (int k = 0; k < 46; ++k) m[k] = 0.0;
     }
-    {
-      const bool up = (lane & 8) != 0;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) {
-        const double hi = (12 + k < 23) ? r1[(12 + k < 23) ? 12 + k : 0] : 0.0;
-        const double keep = up ? hi : r1[k], give = up ? r1[k] : hi;
-        r2[k] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
-      }
-      base += up ? 12 : 0;
-    }
-    {
-      const bool up = (lane & 4) != 0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double keep = up ? r2[6 + k] : r2[k], give = up ? r2[k] : r2[6 + k];
-        r3[k] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-      }
-      base += up ? 6 : 0;
-    }
-    {
-      const bool up = (lane & 2) != 0;
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double keep = up ? r3[3 + k] : r3[k], give = up ? r3[k] : r3[3 + k];
-        r4[k] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
-      }
-      base += up ? 3 : 0;
-    }
-    {
-      const bool up = (lane & 1) != 0;
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const double hi = (k == 0) ? r4[2] : 0.0;
-        const double keep = up ? hi : r4[k], give = up ? r4[k] : hi;
-        r5[k] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
-      }
-      base += up ? 2 : 0;
-    }
-    double* dst = out45 + 45 * static_cast<size_t>(it.cam);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (r5[k] != 0.0) red_add(dst + base + k, r5[k]);   // padding entries are exactly zero and never reach an index >= 45
+    __syncwarp();   // the buffer is refilled by the issue of the next step
+    advance(cp);
+    r_cur = r_nxt;
+    r_nxt = r_pend;
+    r_pend = r_far;
+    stage = stage == 2 ? 0 : stage + 1;
   }
+  cp_async_wait<0>();
 }
 
 }  // namespace b200

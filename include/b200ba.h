@@ -105,6 +105,15 @@ int b200_jacobian_left_multiply(b200_handle* h, const double* x, double* y); /* 
 int b200_model_cost_change(b200_handle* h, const double* step, double* model_cost_change);
 int b200_jacobian_get_values(b200_handle* h, double* values);                /* BlockSparseMatrix::values(), 24N */
 int b200_jacobian_set_values(b200_handle* h, const double* values);          /* mutable_values() */
+/* The four single products of PartitionedMatrixView<2,3,9> (internal/ceres/partitioned_matrix_view_impl.h):
+ *   B200_PMV_RIGHT_E  y[2N] += E x[3P]   (RightMultiplyAndAccumulateE, :113-137)
+ *   B200_PMV_RIGHT_F  y[2N] += F x[9C]   (RightMultiplyAndAccumulateF, :140-191)
+ *   B200_PMV_LEFT_E   y[3P] += E' x[2N]  (LeftMultiplyAndAccumulateE,  :194-264)
+ *   B200_PMV_LEFT_F   y[9C] += F' x[2N]  (LeftMultiplyAndAccumulateF,  :267-375)
+ * On the solver path these only run fused (b200_schur_multiply, b200_jtj_multiply); stand-alone they are the 2x3 / 2x9
+ * block-SpMV shapes of the benchmark sweep.  Single GPU. */
+enum { B200_PMV_RIGHT_E = 0, B200_PMV_RIGHT_F = 1, B200_PMV_LEFT_E = 2, B200_PMV_LEFT_F = 3 };
+int b200_partitioned_multiply(b200_handle* h, int op, const double* x, double* y);
 /* y = (J'J + diag(D)^2) x in one pass over J (D may be NULL).  The normal-equations product CGNR uses
  * (cgnr_solver.cc:90-115); here it is the north-star bandwidth kernel. */
 int b200_jtj_multiply(b200_handle* h, const double* x, const double* D, double* y);

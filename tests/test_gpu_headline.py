@@ -111,5 +111,6 @@ def test_first_lm_iterations_match_oracle(case, oracle_traces, host_boundary):
         for key, floor in (("cost", 1e-6), ("step_norm", 1e-6), ("gradient_max_norm", 1e-6), ("tr_radius", 1e-6)):
             ref = float(b[key])
             spread = abs(float(b2[key]) - ref) / max(abs(ref), 1e-300)
-            tol = min(max(floor, 10.0 * spread), 1e-3)
+            # (one pair of oracle runs is a noisy estimate of the spread: 1e-4 once the solve ran for 50+ CG iterations)
+            tol = min(max(floor, 10.0 * spread, 1e-4 if int(b["ls_iterations"]) >= 50 else 0.0), 1e-3)
             assert abs(a[key] - ref) <= tol * max(abs(ref), 1e-300), (key, a[key], ref, spread, a["iteration"])

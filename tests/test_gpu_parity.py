@@ -123,6 +123,12 @@ def test_sparse_matrix_ops(c16_case):
     expect = J.left_multiply(J.right_multiply(x)) + D * D * x
     assert relerr(case.gpu.jtj_multiply(x, D), expect) < 1e-12
     assert relerr(case.gpu.jtj_multiply(x, None), J.left_multiply(J.right_multiply(x))) < 1e-12
+    # PartitionedMatrixView<2,3,9> single products (partitioned_matrix_view_test.cc: against the full products)
+    P, C = case.gpu.P, case.gpu.C
+    xe, xf = x[:3 * P], x[3 * P:]
+    assert relerr(case.gpu.partitioned_multiply(0, xe) + case.gpu.partitioned_multiply(1, xf), J.right_multiply(x)) < 1e-13
+    assert relerr(case.gpu.partitioned_multiply(0, xe), J.pmv(P, 0, xe, case.gpu.num_residuals)) < 1e-13
+    assert relerr(np.concatenate([case.gpu.partitioned_multiply(2, y), case.gpu.partitioned_multiply(3, y)]), J.left_multiply(y)) < 1e-12
     s = 1.0 / (1.0 + np.sqrt(J.squared_column_norm()))
     case.gpu.scale_columns(s)
     J.scale_columns(s, nt=8)
