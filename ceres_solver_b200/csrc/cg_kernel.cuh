@@ -86,6 +86,7 @@ struct CgVecArgs {
   XchgPeers xg;                // xg.world == 0: single GPU / q already complete
   int xg_slot;
   unsigned xg_epoch;
+  int pdl;                     // launched as a programmatic dependent of the product: wait for it before touching q / p.q
   unsigned* bar;               // {arrival count, generation}: grid barrier of an ORDINARY launch (all CTAs co-resident: the
                                // grid is at most one CTA per SM and the stream holds nothing else while it runs); null: the
                                // kernel was launched cooperatively and uses cooperative-groups grid.sync()
@@ -187,19 +188,10 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
   double pj = 0.0, qj = 0.0, xj = 0.0, rj = 0.0, bj = 0.0, dj = 0.0;
   double mrow[9];
   double pq_pre = 0.0;  // this lane's share of the fused p.q partials (warps 0 and 1)
-  if (a.pq_parts != nullptr && (mode == CG_NORMAL || mode == CG_RESET_FIRST)) {
-    const int warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) {
-      for (int b = lane; b < a.num_pq_parts; b += 32) pq_pre += __ldcg(a.pq_parts + b);
-    } else if (warp == 1) {
-      for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) pq_pre += __ldcg(a.seed_pq + b);
-    }
-  }
   if (ok0) {
     bj = a.rhs[j0];
     if (mode != CG_BEGIN) {
       pj = a.p[j0];
-      if (a.xg.world <= 1) qj = a.q[j0];
       xj = a.x[j0];
       if (mode != CG_RESET_SECOND) rj = a.r[j0];
     }
@@ -211,6 +203,18 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       for (int k = 0; k < 9; ++k) mrow[k] = m[k];
     }
   }
+  // Everything above is complete before the product of this iteration even started (the product waited for the previous
+  // vector kernel before it let this one launch); what follows is what the product wrote.
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (a.pq_parts != nullptr && (mode == CG_NORMAL || mode == CG_RESET_FIRST)) {
+    const int warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) {
+      for (int b = lane; b < a.num_pq_parts; b += 32) pq_pre += __ldcg(a.pq_parts + b);
+    } else if (warp == 1) {
+      for (int b = lane; b < static_cast<int>(gridDim.x); b += 32) pq_pre += __ldcg(a.seed_pq + b);
+    }
+  }
+  if (ok0 && mode != CG_BEGIN && a.xg.world <= 1) qj = __ldcg(a.q + j0);
 
   if (mode != CG_BEGIN && st_done) return;
   if (a.xg.world > 1 && mode != CG_BEGIN) {

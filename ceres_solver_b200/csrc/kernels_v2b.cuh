@@ -528,12 +528,13 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------------
 // Camera-major block diagonal (no atomics on the hot loop).  For a row i of point k (no camera seeing a point twice):
 //   F_i'F_i - (E_i'F_i)' P_k (E_i'F_i) = F_i' Q_i F_i ,   Q_i = I - E_i P_k E_i'   (2x2 symmetric)
-// so  M_c = sum_{i in camera c} F_i' Q_i F_i.  row_q_kernel writes Q_i (3 doubles per row) in one flat pass over E;
-// cam_blocks_kernel gives every warp a slice of one camera's row list (the transpose block structure of the
-// reference, block_sparse_matrix.cc:784-808), keeps the 45 packed entries in registers while it walks the rows, and
-// adds its slice total with 45 REDs.  Same result as SchurEliminator against a block-diagonal lhs
+// so  M_c = sum_{i in camera c} F_i' Q_i F_i.  Q_i (q00, q01, q11 + one pad per row) is written by the implicit-Schur
+// initialisation (kernels_v4b.cuh) or, on the fallback paths, by row_q_kernel in one flat pass over E; the camera-major
+// kernels of kernels_v4b.cuh keep the 45 packed entries in registers while they walk a camera's rows.  Same result as SchurEliminator against a block-diagonal lhs
 // (schur_eliminator_impl.h:449-568) / UpdateBlockDiagonalFtF (partitioned_matrix_view_impl.h:531-658, Q = I).
 // ------------------------------------------------------------------------------------------------
+constexpr int kQStride = 4;   // doubles per row of the Q array: q00, q01, q11 and one pad (32-byte rows: aligned bulk copies)
+
 __global__ void __launch_bounds__(256) row_q_kernel(ProblemView p, const double* __restrict__ ete_inv, double* q3) {
   const int stride = gridDim.x * blockDim.x;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < p.N; r += stride) {
@@ -545,9 +546,9 @@ __global__ void __launch_bounds__(256) row_q_kernel(ProblemView p, const double*
     // P e_r' for both rows of E
     const double a = p0 * e00 + p1 * e01 + p2 * e02, b = p1 * e00 + p3 * e01 + p4 * e02, c = p2 * e00 + p4 * e01 + p5 * e02;
     const double d = p0 * e10 + p1 * e11 + p2 * e12, e = p1 * e10 + p3 * e11 + p4 * e12, f = p2 * e10 + p4 * e11 + p5 * e12;
-    q3[3 * static_cast<size_t>(r) + 0] = 1.0 - (e00 * a + e01 * b + e02 * c);
-    q3[3 * static_cast<size_t>(r) + 1] = -(e10 * a + e11 * b + e12 * c);
-    q3[3 * static_cast<size_t>(r) + 2] = 1.0 - (e10 * d + e11 * e + e12 * f);
+    double2* q = reinterpret_cast<double2*>(q3 + kQStride * static_cast<size_t>(r));
+    q[0] = make_double2(1.0 - (e00 * a + e01 * b + e02 * c), -(e10 * a + e11 * b + e12 * c));
+    q[1] = make_double2(1.0 - (e10 * d + e11 * e + e12 * f), 0.0);
   }
 }
 
@@ -555,58 +556,5 @@ struct CamItem {
   int cam;
   int begin, end;  // range in cam_rows
 };
-
-template <bool kSchur>
-__global__ void __launch_bounds__(256, 1)
-    cam_blocks_kernel(ProblemView p, int num_items, const CamItem* __restrict__ items, const int* __restrict__ cam_rows,
-                      const double* __restrict__ q3, double* out45) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < num_items; item += gridDim.x * warps_per_block) {
-    const CamItem it = items[item];
-    double m[45];
-#pragma unroll
-    for (int k = 0; k < 45; ++k) m[k] = 0.0;
-    for (int j = it.begin + lane; j < it.end; j += 32) {
-      const int r = cam_rows[j];
-      const double2* fp = reinterpret_cast<const double2*>(p.F() + 18 * static_cast<size_t>(r));
-      double f[18];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double2 w = __ldg(fp + k);
-        f[2 * k] = w.x;
-        f[2 * k + 1] = w.y;
-      }
-      double q00 = 1.0, q01 = 0.0, q11 = 1.0;
-      if (kSchur) {
-        q00 = q3[3 * static_cast<size_t>(r)];
-        q01 = q3[3 * static_cast<size_t>(r) + 1];
-        q11 = q3[3 * static_cast<size_t>(r) + 2];
-      }
-      double g0[9], g1[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        g0[k] = q00 * f[k] + q01 * f[9 + k];
-        g1[k] = q01 * f[k] + q11 * f[9 + k];
-      }
-      int idx = 0;
-#pragma unroll
-      for (int aa = 0; aa < 9; ++aa) {
-#pragma unroll
-        for (int bb = aa; bb < 9; ++bb) {
-          m[idx] += f[aa] * g0[bb] + f[9 + aa] * g1[bb];
-          ++idx;
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 45; ++k) {
-      double v = m[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && v != 0.0) red_add(out45 + 45 * static_cast<size_t>(it.cam) + k, v);
-    }
-  }
-}
 
 }  // namespace b200

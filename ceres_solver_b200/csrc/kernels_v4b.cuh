@@ -15,7 +15,7 @@ struct InitV4Args {
   double* ete_inv;   // [6P]
   double* rhs;       // [9C], zeroed by the caller
   double* ye;        // [3P] or null
-  double* q3;        // [3N] or null: Q_r = I - E_r (E'E + D^2)^-1 E_r'  (2x2 symmetric: q00, q01, q11) per row
+  double* q3;        // [kQStride N] or null: Q_r = I - E_r (E'E + D^2)^-1 E_r'  (2x2 symmetric: q00, q01, q11, pad) per row
 };
 
 // slot: [0,4608) F | [4608,6144) E | [6144,6656) b (16 B per row) | [6656,7440) the tile's slice of D_e (24 B per point, the
@@ -151,10 +151,9 @@ __device__ __forceinline__ void init_big_points_impl(const V2View& v, const BigS
                      pc = inv[2] * e0.x + inv[4] * e0.y + inv[5] * e1.x;
         const double pd = inv[0] * e1.y + inv[1] * e2.x + inv[2] * e2.y, pe = inv[1] * e1.y + inv[3] * e2.x + inv[4] * e2.y,
                      pf = inv[2] * e1.y + inv[4] * e2.x + inv[5] * e2.y;
-        double* q = a.q3 + 3 * row;
-        q[0] = 1.0 - (e0.x * pa + e0.y * pb + e1.x * pc);
-        q[1] = -(e1.y * pa + e2.x * pb + e2.y * pc);
-        q[2] = 1.0 - (e1.y * pd + e2.x * pe + e2.y * pf);
+        double2* q = reinterpret_cast<double2*>(a.q3 + kQStride * row);
+        q[0] = make_double2(1.0 - (e0.x * pa + e0.y * pb + e1.x * pc), -(e1.y * pa + e2.x * pb + e2.y * pc));
+        q[1] = make_double2(1.0 - (e1.y * pd + e2.x * pe + e2.y * pf), 0.0);
       }
     }
     __syncthreads();  // staging and sU are reused by the next point
@@ -274,10 +273,9 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1) schur_init_v4_kernel(V2View 
                      pc = inv[2] * e0.x + inv[4] * e0.y + inv[5] * e1.x;
         const double pd = inv[0] * e1.y + inv[1] * e2.x + inv[2] * e2.y, pe = inv[1] * e1.y + inv[3] * e2.x + inv[4] * e2.y,
                      pf = inv[2] * e1.y + inv[4] * e2.x + inv[5] * e2.y;
-        double* q = a.q3 + 3 * (static_cast<size_t>(row_begin) + lane);
-        q[0] = 1.0 - (e0.x * pa + e0.y * pb + e1.x * pc);
-        q[1] = -(e1.y * pa + e2.x * pb + e2.y * pc);
-        q[2] = 1.0 - (e1.y * pd + e2.x * pe + e2.y * pf);
+        double2* q = reinterpret_cast<double2*>(a.q3 + kQStride * (static_cast<size_t>(row_begin) + lane));
+        q[0] = make_double2(1.0 - (e0.x * pa + e0.y * pb + e1.x * pc), -(e1.y * pa + e2.x * pb + e2.y * pc));
+        q[1] = make_double2(1.0 - (e1.y * pd + e2.x * pe + e2.y * pf), 0.0);
       }
     }
     if (kOwned) cam_accumulate9_owned(my_y, cam_l, active, g);
@@ -314,9 +312,9 @@ __global__ void __launch_bounds__(kTile) row_q_tiles_kernel(ProblemView p, const
     const double p0 = __ldg(pi), p1 = __ldg(pi + 1), p2 = __ldg(pi + 2), p3 = __ldg(pi + 3), p4 = __ldg(pi + 4), p5 = __ldg(pi + 5);
     const double a = p0 * e00 + p1 * e01 + p2 * e02, b = p1 * e00 + p3 * e01 + p4 * e02, c = p2 * e00 + p4 * e01 + p5 * e02;
     const double dd = p0 * e10 + p1 * e11 + p2 * e12, e = p1 * e10 + p3 * e11 + p4 * e12, f = p2 * e10 + p4 * e11 + p5 * e12;
-    q3[3 * r + 0] = 1.0 - (e00 * a + e01 * b + e02 * c);
-    q3[3 * r + 1] = -(e10 * a + e11 * b + e12 * c);
-    q3[3 * r + 2] = 1.0 - (e10 * dd + e11 * e + e12 * f);
+    double2* q = reinterpret_cast<double2*>(q3 + kQStride * r);
+    q[0] = make_double2(1.0 - (e00 * a + e01 * b + e02 * c), -(e10 * a + e11 * b + e12 * c));
+    q[1] = make_double2(1.0 - (e10 * dd + e11 * e + e12 * f), 0.0);
   }
 }
 
@@ -330,14 +328,11 @@ __global__ void __launch_bounds__(kTile) row_q_tiles_kernel(ProblemView p, const
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-constexpr int kCamBlkRowBytes = 144 + 24;                 // F row + Q block
+constexpr int kCamBlkRowBytes = 144 + 32;                 // F row + Q block (q00, q01, q11, pad)
 constexpr int kCamBlkDepth = 3;                           // buffers per warp: data of two steps in flight behind the one computed
 constexpr int kCamBlkWarpBytes = kCamBlkDepth * 32 * kCamBlkRowBytes;
 constexpr int kCamBlkThreads = 128;
@@ -445,11 +440,10 @@ __global__ void __launch_bounds__(kCamBlkThreads, 3)
 #pragma unroll
       for (int k = 0; k < 9; ++k) cp_async16(dst + 16 * k, src + 16 * k);
       if (kSchur) {
-        unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24;
-        const double* sq = q3 + 3 * static_cast<size_t>(r);
-        cp_async8(dq, sq);
-        cp_async8(dq + 8, sq + 1);
-        cp_async8(dq + 16, sq + 2);
+        unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 32;
+        const double* sq = q3 + kQStride * static_cast<size_t>(r);
+        cp_async16(dq, sq);
+        cp_async16(dq + 16, sq + 2);
       }
     }
     cp_async_commit();
@@ -487,7 +481,7 @@ __global__ void __launch_bounds__(kCamBlkThreads, 3)
       }
       double q00 = 1.0, q01 = 0.0, q11 = 1.0;
       if (kSchur) {
-        const double* q = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + 32 * 144 + lane * 24);
+        const double* q = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + 32 * 144 + lane * 32);
         q00 = q[0];
         q01 = q[1];
         q11 = q[2];
@@ -516,6 +510,168 @@ __global__ void __launch_bounds__(kCamBlkThreads, 3)
     stage = stage == 2 ? 0 : stage + 1;
   }
   cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Camera-major block diagonal, CTA-local (third version).  The gather version above reads every F row exactly once but in
+// camera-major order, i.e. as 144-byte pieces scattered over the whole array: measured 2.9 TB/s at best, whatever the
+// latency hiding (register, cp.async double buffer, continuous stream: 42-48 us on Ladybug-1723).  Here every persistent CTA
+// STREAMS its own contiguous row range (the same partition as the warp-tile kernels) through shared memory in chunks of up to
+// 512 rows -- two bulk copies per chunk, DRAM sees a linear read -- and the regrouping by camera happens on chip: the host
+// sorted the rows of every chunk by camera once (b200_create), a quarter-warp takes one (camera, chunk) segment, its eight
+// lanes walk the segment's rows in shared memory with the 45 packed entries in registers, reduce them by recursive halving
+// over the eight lanes and add the result to the CTA's private accumulator of that camera (plain read-modify-write: a
+// segment has exactly one owner and chunks are separated by a CTA barrier).  One flush of <= span x 45 REDs per CTA.
+// ------------------------------------------------------------------------------------------------
+struct CbChunk {
+  int row_begin, row_count;   // rows of the chunk (<= kCbChunkRows)
+  int seg_begin, seg_count;   // its (camera, chunk) segments in CbView::segs, longest first (<= kCbMaxSegs)
+  int slot_begin;             // its sorted row slots in CbView::slots (multiple of 8)
+  int pad0, pad1, pad2;
+};
+struct CbView {
+  const CbChunk* chunks;
+  const int2* cta_chunks;     // per CTA: [begin, end) into chunks
+  const uint2* segs;          // x = camera position in the CTA's list | rows << 16 ; y = offset into the chunk's slot list
+  const unsigned short* slots;
+};
+constexpr int kCbChunkRows = 512;
+constexpr int kCbMaxSegs = 128;
+constexpr int kCbThreads = 256;
+constexpr int kCbBufBytes = kCbChunkRows * 144 + kCbChunkRows * 32 + kCbMaxSegs * 8 + kCbChunkRows * 2;
+__host__ __device__ inline size_t cb3_acc_bytes(int max_cam_span) { return (static_cast<size_t>(45) * max_cam_span * 8 + 127) & ~static_cast<size_t>(127); }
+__host__ __device__ inline size_t cb3_smem_bytes(int max_cam_span) { return cb3_acc_bytes(max_cam_span) + 2 * kCbBufBytes + 64; }
+
+template <bool kSchur>
+__global__ void __launch_bounds__(kCbThreads, 1)
+    cam_blocks_v3_kernel(V2View v, CbView cb, const double* __restrict__ q3, double* out45) {
+  extern __shared__ __align__(128) unsigned char cb_smem[];
+  double* sacc = reinterpret_cast<double*>(cb_smem);
+  unsigned char* bufs = cb_smem + cb3_acc_bytes(v.max_cam_span);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bufs + 2 * kCbBufBytes);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int2 cr = v.cta_cam[blockIdx.x];
+  const int2 cc = cb.cta_chunks[blockIdx.x];
+  const int nacc = 45 * v2_span(v, cr);
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.0;
+  if (threadIdx.x == 0) {
+    mbar_init(bars, 1);
+    mbar_init(bars + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {   // thread 0: chunk k of this CTA -> buffer k & 1
+    const CbChunk ch = cb.chunks[cc.x + k];
+    unsigned char* buf = bufs + (k & 1) * kCbBufBytes;
+    uint64_t* bar = bars + (k & 1);
+    const uint32_t fb = ch.row_count * 144u, qb = kSchur ? ch.row_count * 32u : 0u;
+    const uint32_t sb = ((ch.seg_count * 8u) + 15u) & ~15u, lb = ((ch.row_count * 2u) + 15u) & ~15u;
+    mbar_arrive_expect_tx(bar, fb + qb + sb + lb);
+    bulk_g2s(buf, v.p.F() + 18 * static_cast<size_t>(ch.row_begin), fb, bar);
+    if (kSchur) bulk_g2s(buf + kCbChunkRows * 144, q3 + kQStride * static_cast<size_t>(ch.row_begin), qb, bar);
+    bulk_g2s(buf + kCbChunkRows * 176, cb.segs + ch.seg_begin, sb, bar);
+    bulk_g2s(buf + kCbChunkRows * 176 + kCbMaxSegs * 8, cb.slots + ch.slot_begin, lb, bar);
+  };
+  const int nchunks = cc.y - cc.x;
+  if (threadIdx.x == 0) {
+    if (nchunks > 0) issue(0);
+    if (nchunks > 1) issue(1);
+  }
+  const int quarter = lane >> 3, sub = lane & 7;
+  const int base = ((lane & 4) ? 24 : 0) + ((lane & 2) ? 12 : 0) + ((lane & 1) ? 6 : 0);
+  for (int k = 0; k < nchunks; ++k) {
+    const int seg_count = cb.chunks[cc.x + k].seg_count;   // (L2 hit; in flight while the chunk lands)
+    const unsigned char* buf = bufs + (k & 1) * kCbBufBytes;
+    const double* sF = reinterpret_cast<const double*>(buf);
+    const double* sQ = reinterpret_cast<const double*>(buf + kCbChunkRows * 144);
+    const uint2* sSeg = reinterpret_cast<const uint2*>(buf + kCbChunkRows * 176);
+    const unsigned short* sSlot = reinterpret_cast<const unsigned short*>(buf + kCbChunkRows * 176 + kCbMaxSegs * 8);
+    mbar_wait(bars + (k & 1), (k >> 1) & 1);
+    for (int s0 = 0; s0 < seg_count; s0 += 4 * (kCbThreads / 32)) {
+      const int sidx = s0 + warp * 4 + quarter;
+      int cam_l = 0, count = 0, slot0 = 0;
+      if (sidx < seg_count) {
+        const uint2 sg = sSeg[sidx];
+        cam_l = static_cast<int>(sg.x & 0xffffu);
+        count = static_cast<int>(sg.x >> 16);
+        slot0 = static_cast<int>(sg.y);
+      }
+      int cmax = count;
+#pragma unroll
+      for (int o = 16; o >= 8; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      double m[48];
+#pragma unroll
+      for (int q = 0; q < 48; ++q) m[q] = 0.0;
+      for (int i = sub; i < cmax; i += 8) {
+        if (i < count) {
+          const int slot = sSlot[slot0 + i];
+          const double* fr = sF + slot * 18;
+          double f[18];
+#pragma unroll
+          for (int q = 0; q < 9; ++q) {
+            const double2 w = lds2(fr + 2 * q);
+            f[2 * q] = w.x;
+            f[2 * q + 1] = w.y;
+          }
+          double q00 = 1.0, q01 = 0.0, q11 = 1.0;
+          if (kSchur) {
+            const double2 qa = lds2(sQ + slot * 4), qb2 = lds2(sQ + slot * 4 + 2);
+            q00 = qa.x;
+            q01 = qa.y;
+            q11 = qb2.x;
+          }
+          int idx = 0;
+#pragma unroll
+          for (int aa = 0; aa < 9; ++aa) {
+            const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
+#pragma unroll
+            for (int bb = aa; bb < 9; ++bb) {
+              m[idx] += ga * f[bb] + gb * f[9 + bb];
+              ++idx;
+            }
+          }
+        }
+      }
+      // recursive halving over the eight lanes of the quarter: 48 -> 24 -> 12 -> 6 entries per lane
+      double r1[24], r2[12], r3[6];
+      {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int q = 0; q < 24; ++q) {
+          const double keep = up ? m[24 + q] : m[q], give = up ? m[q] : m[24 + q];
+          r1[q] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+        }
+      }
+      {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int q = 0; q < 12; ++q) {
+          const double keep = up ? r1[12 + q] : r1[q], give = up ? r1[q] : r1[12 + q];
+          r2[q] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+        }
+      }
+      {
+        const bool up = (lane & 1) != 0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const double keep = up ? r2[6 + q] : r2[q], give = up ? r2[q] : r2[6 + q];
+          r3[q] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
+        }
+      }
+      if (sidx < seg_count) {
+        double* acc = sacc + 45 * cam_l + base;
+#pragma unroll
+        for (int q = 0; q < 6; ++q)
+          if (base + q < 45) acc[q] += r3[q];
+      }
+    }
+    __syncthreads();   // every warp is done with the buffer (and with this chunk's accumulator updates)
+    if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
+  }
+  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
+    const double acc = sacc[i];
+    if (acc != 0.0) red_add(out45 + v2_global_entry(v, cr, i, 45), acc);
+  }
 }
 
 }  // namespace b200

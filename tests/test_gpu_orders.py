@@ -150,22 +150,7 @@ def oracle_traces(case):
 
 @pytest.mark.parametrize("host_boundary", [False, True])
 def test_lm_trajectory(case, oracle_traces, host_boundary):
+    from conftest import compare_lm_traces
     (state_o, recs_o), (state_o2, recs_o2) = oracle_traces
     state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(max_num_iterations=4), host_boundary=host_boundary)
-    assert len(recs) == len(recs_o)
-    exact = True
-    for a, b, b2 in zip(recs, recs_o, recs_o2):
-        if int(b["ls_iterations"]) != int(b2["ls_iterations"]) or int(b["step_is_successful"]) != int(b2["step_is_successful"]):
-            break   # the oracle's own trajectory forks here under a change of summation order: nothing left to compare
-        assert a["ls_iterations"] == int(b["ls_iterations"]), (a, b)
-        assert a["step_is_successful"] == int(b["step_is_successful"])
-        for key in ("cost", "step_norm"):
-            ref = float(b[key])
-            spread = abs(float(b2[key]) - ref) / max(abs(ref), 1e-300)
-            # one pair of oracle runs is a noisy estimate of the spread; once the inexact solve has run for 50+ CG iterations
-            # the oracle's own numbers move at the 1e-5 level (2e-5 measured at 117 iterations on ladybug-1723)
-            tol = min(max(1e-6, 10.0 * spread, 1e-4 if int(b["ls_iterations"]) >= 50 else 0.0), 1e-2)
-            exact = exact and tol == 1e-6
-            assert abs(a[key] - ref) <= tol * max(abs(ref), 1e-300), (key, a[key], ref, spread, a["iteration"])
-    spread_state = relerr(state_o2, state_o)
-    assert relerr(state, state_o) < max(1e-6, 10.0 * spread_state, 1e-5)
+    compare_lm_traces(recs, recs_o, recs_o2, keys=("cost", "step_norm"))
