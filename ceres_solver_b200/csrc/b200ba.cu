@@ -291,16 +291,8 @@ struct b200_handle {
   CamItem* d_cam_items = nullptr;
   int* d_cam_rows = nullptr;
   double* d_q3 = nullptr;
-  // CTA-local camera-major blocks (cam_blocks_v3_kernel): per-CTA chunk lists, (camera, chunk) segments, sorted row slots
-  bool cb3_ok = false;
-  CbChunk* d_cb_chunks = nullptr;
-  int2* d_cb_cta = nullptr;
-  uint2* d_cb_segs = nullptr;
-  unsigned short* d_cb_slots = nullptr;
-  CbView cb3{};
   double* d_ybig = nullptr;   // RED target of the big-point kernel inside the PCG (consumed + zeroed by cg_vector_kernel)
   double* d_red = nullptr;    // per-CTA partial sums of cg_vector_kernel
-  unsigned* d_cg_bar = nullptr;  // grid barrier words of cg_vector_kernel
   // multi-GPU exchange of the per-iteration partial products over NVLink peer memory (cg_kernel.cuh: xchg_push_kernel +
   // the gather in cg_vector_kernel); replaces the ncclAllReduce inside the PCG iteration when every peer could be mapped
   bool xchg_ok = false;
@@ -668,14 +660,6 @@ int precond_update_dev(b200_handle* h, int type) {
       OK(launch(h, K_DIAG_BLOCKS, [&] {
         row_q_kernel<<<flat_grid(h, h->N, 256), 256, 0, h->stream>>>(h->view, h->d_ete_inv, h->d_q3);
       }, false));
-    if (h->cb3_ok && h->v2_ok) {
-      // CTA-local streaming pass (needs Q_r of every row: written by the init kernel, or by row_q_kernel just above)
-      OK(launch(h, K_DIAG_BLOCKS, [&] {
-        const size_t smem = cb3_smem_bytes(h->v2.max_cam_span);
-        if (schur) cam_blocks_v3_kernel<true><<<h->v2.num_ctas, kCbThreads, smem, h->stream>>>(h->v2, h->cb3, h->d_q3, h->d_upper45);
-        else cam_blocks_v3_kernel<false><<<h->v2.num_ctas, kCbThreads, smem, h->stream>>>(h->v2, h->cb3, h->d_q3, h->d_upper45);
-      }));
-    } else
     OK(launch(h, K_DIAG_BLOCKS, [&] {
       const int g = std::max(1, std::min((h->num_cam_items + 3) / 4, h->sm_count * 12));
       const size_t smem = static_cast<size_t>(kCamBlkThreads / 32) * kCamBlkWarpBytes;
@@ -773,31 +757,6 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
       va.xg = h->xpeers;
       va.xg_slot = static_cast<int>(h->xepoch & 1u);
       va.xg_epoch = h->xepoch;
-    }
-    va.bar = nullptr;
-    va.pdl = 0;
-    if (dev_env("B200_CG_SOFT_BARRIER") != nullptr) {   // A/B: ordinary launch + grid barrier in global memory (3 % slower)
-      va.bar = h->d_cg_bar;
-      return launch(h, K_CG_VEC, [&] { cg_vector_kernel<<<h->cg_grid, kCgThreads, 0, h->stream>>>(va); });
-    }
-    if (dev_env("B200_CG_PDL") != nullptr && !h->profiling) {
-      // A/B: ordinary launch + global-memory grid barrier, launched as a programmatic dependent of the product before it:
-      // its launch latency and operand loads overlap the product's tail
-      va.bar = h->d_cg_bar;
-      va.pdl = 1;
-      return launch(h, K_CG_VEC, [&] {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(h->cg_grid);
-        cfg.blockDim = dim3(kCgThreads);
-        cfg.dynamicSmemBytes = 0;
-        cfg.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, cg_vector_kernel, va);
-      });
     }
     void* args[] = {&va};
     return launch(h, K_CG_VEC, [&] {
@@ -1463,11 +1422,6 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   const int num_ctas_v2 = prop.multiProcessorCount;
   std::vector<int2> cta_part(num_ctas_v2), cta_cam(num_ctas_v2), cta_big(num_ctas_v2, make_int2(0, 0));
   std::vector<int> cta_cams;   // direct mode: concatenated per-CTA camera lists
-  std::vector<CbChunk> cb_chunks;
-  std::vector<int2> cb_cta;
-  std::vector<uint2> cb_segs;
-  std::vector<unsigned short> cb_slots;
-  bool cb3_possible = false;
   bool direct_mode = false;
   int max_cam_span = 1, v2_warps = 0, v2_stages = 0, v2_replicas = 1, mul_warps = 0, mul_stages = 0, mul_replicas = 1;
   if (v2_possible && !wtiles.empty()) {
@@ -1565,77 +1519,6 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
         max_cam_span = max_range;
         for (int b = 0; b < num_ctas_v2; ++b) cta_cam[b] = make_int2(lo_v[b], hi_v[b]);
       }
-    }
-    // CTA-local camera-major pass (cam_blocks_v3_kernel): every CTA's contiguous row range cut into chunks of <= 512 rows, the
-    // rows of a chunk sorted by camera (position in the CTA's list), one segment per (camera, chunk), longest first.
-    if (direct_mode && !has_dups && huge_pts.empty() && cb3_smem_bytes(max_cam_span) <= static_cast<size_t>(prop.sharedMemPerBlockOptin) - 1024 &&
-        dev_env("B200_NO_CB3") == nullptr) {
-      long covered = 0;
-      bool contiguous = true;
-      int prev_end = 0;
-      cb_cta.assign(num_ctas_v2, make_int2(0, 0));
-      std::vector<std::pair<int, int>> order;   // (camera position, row) of the current chunk
-      for (int b = 0; b < num_ctas_v2 && contiguous; ++b) {
-        int lo = N, hi = 0;
-        for (int t = cta_part[b].x; t < cta_part[b].y; ++t) {
-          lo = std::min(lo, wtiles[t].row_begin);
-          hi = std::max(hi, wtiles[t].row_begin + wtiles[t].row_count);
-        }
-        for (int g = cta_big[b].x; g < cta_big[b].y; ++g) {
-          lo = std::min(lo, big_tiles[g].obs_begin);
-          hi = std::max(hi, big_tiles[g].obs_begin + big_tiles[g].obs_count);
-        }
-        cb_cta[b].x = static_cast<int>(cb_chunks.size());
-        if (hi > lo) {
-          if (lo != prev_end) contiguous = false;
-          prev_end = hi;
-          covered += hi - lo;
-          int r = lo;
-          while (r < hi) {
-            int rows = std::min(kCbChunkRows, hi - r);
-            for (;;) {   // at most kCbMaxSegs distinct cameras per chunk
-              order.clear();
-              for (int i = 0; i < rows; ++i) order.emplace_back(static_cast<int>((row_meta[r + i] >> kMetaLocalShift) & kMetaLocalMask), r + i);
-              std::stable_sort(order.begin(), order.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& c) { return a.first < c.first; });
-              int distinct = 0;
-              for (int i = 0; i < rows; ++i)
-                if (i == 0 || order[i].first != order[i - 1].first) ++distinct;
-              if (distinct <= kCbMaxSegs) break;
-              rows = rows / 2;
-            }
-            // segments, longest first
-            std::vector<std::array<int, 3>> seg;   // {count, cam position, first index in `order`}
-            for (int i = 0; i < rows;) {
-              int j = i;
-              while (j < rows && order[j].first == order[i].first) ++j;
-              seg.push_back({j - i, order[i].first, i});
-              i = j;
-            }
-            std::stable_sort(seg.begin(), seg.end(), [](const std::array<int, 3>& a, const std::array<int, 3>& c) { return a[0] > c[0]; });
-            CbChunk ch{};
-            ch.row_begin = r;
-            ch.row_count = rows;
-            while (cb_segs.size() % 2 != 0) cb_segs.push_back(make_uint2(0u, 0u));
-            while (cb_slots.size() % 8 != 0) cb_slots.push_back(0);
-            ch.seg_begin = static_cast<int>(cb_segs.size());
-            ch.seg_count = static_cast<int>(seg.size());
-            ch.slot_begin = static_cast<int>(cb_slots.size());
-            int off = 0;
-            for (const auto& sgm : seg) {
-              cb_segs.push_back(make_uint2(static_cast<uint32_t>(sgm[1]) | (static_cast<uint32_t>(sgm[0]) << 16), static_cast<uint32_t>(off)));
-              for (int i = 0; i < sgm[0]; ++i) cb_slots.push_back(static_cast<unsigned short>(order[sgm[2] + i].second - r));
-              off += sgm[0];
-            }
-            cb_chunks.push_back(ch);
-            r += rows;
-          }
-        }
-        cb_cta[b].y = static_cast<int>(cb_chunks.size());
-      }
-      cb3_possible = contiguous && covered == N;
-      // (bulk copies read up to 15 bytes past a chunk's lists)
-      for (int i = 0; i < 4; ++i) cb_segs.push_back(make_uint2(0u, 0u));
-      for (int i = 0; i < 16; ++i) cb_slots.push_back(0);
     }
     // Shared memory budget: `replicas` private camera vectors + per-warp {TMA ring of F cells, exchange scratch}.
     // Prefer one replica per warp (no cross-warp contention) when the camera span of a CTA is small.
@@ -1800,24 +1683,6 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     CU(cudaMemcpyAsync(h->d_cam_rows, cam_rows.data(), n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->cam_major_ok = true;
-    if (cb3_possible) {
-      OK(dev_alloc(&h->d_cb_chunks, cb_chunks.size()));
-      OK(dev_alloc(&h->d_cb_cta, cb_cta.size()));
-      OK(dev_alloc(&h->d_cb_segs, cb_segs.size()));
-      OK(dev_alloc(&h->d_cb_slots, cb_slots.size()));
-      CU(cudaMemcpyAsync(h->d_cb_chunks, cb_chunks.data(), cb_chunks.size() * sizeof(CbChunk), cudaMemcpyHostToDevice, h->stream));
-      CU(cudaMemcpyAsync(h->d_cb_cta, cb_cta.data(), cb_cta.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-      CU(cudaMemcpyAsync(h->d_cb_segs, cb_segs.data(), cb_segs.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
-      CU(cudaMemcpyAsync(h->d_cb_slots, cb_slots.data(), cb_slots.size() * sizeof(unsigned short), cudaMemcpyHostToDevice, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      h->cb3.chunks = h->d_cb_chunks;
-      h->cb3.cta_chunks = h->d_cb_cta;
-      h->cb3.segs = h->d_cb_segs;
-      h->cb3.slots = h->d_cb_slots;
-      CU(cudaFuncSetAttribute(cam_blocks_v3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-      CU(cudaFuncSetAttribute(cam_blocks_v3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prop.sharedMemPerBlockOptin) - 1024));
-      h->cb3_ok = true;
-    }
   }
   h->num_huge = static_cast<int>(huge_pts.size());
   if (h->num_huge > 0) {
@@ -2018,10 +1883,10 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   }
   if (getenv("B200_VERBOSE") != nullptr)
     fprintf(stderr,
-            "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d cb3=%d\n",
+            "[b200ba] C=%d P=%d N=%d wtiles=%zu big(+slices)=%zu huge=%d span=%d direct=%d v2(w=%d,s=%d,r=%d) mul(%s w=%d,s=%d,r=%d,smem=%zu) folded=%d v2b=%d cam_major=%d\n",
             C, P, N, wtiles.size(), big_tiles.size(), h->num_huge, max_cam_span, h->v2.direct, h->v2.warps, h->v2.stages, h->v2.replicas,
             h->mul_v4 ? (h->mul_v4_owned ? "v4-owned" : "v4") : (h->mul_v3 ? "v3" : "v2"), h->v2_mul.warps, h->v2_mul.stages, h->v2_mul.replicas, h->mul_smem,
-            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0, h->cb3_ok ? 1 : 0);
+            h->big_folded ? 1 : 0, h->v2b_ok ? 1 : 0, h->cam_major_ok ? 1 : 0);
   for (int k = 0; k < K_COUNT; ++k) h->grid_tile[k] = std::max(1, std::min(h->num_tiles, h->sm_count * 4));
   h->grid_tile[K_EVAL_JAC] = tile_grid(h, evaluate_kernel<true>, tile_smem_bytes<3, 1>());
   h->grid_tile[K_EVAL_COST] = tile_grid(h, evaluate_kernel<false>, tile_smem_bytes<3, 1>());
@@ -2038,11 +1903,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cg_vector_kernel, kCgThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
     const int nblocks = (C + kCgCamsPerCta - 1) / kCgCamsPerCta;
-    (void)per_sm;  // one CTA per SM at most: the ordinary-launch grid barrier needs every CTA resident
-    h->cg_grid = std::max(1, std::min(nblocks, h->sm_count));
+    h->cg_grid = std::max(1, std::min(nblocks, per_sm * h->sm_count));
     OK(dev_alloc(&h->d_red, static_cast<size_t>(h->cg_grid) * 4));
-    OK(dev_alloc(&h->d_cg_bar, 4));
-    CU(cudaMemsetAsync(h->d_cg_bar, 0, 4 * sizeof(unsigned), h->stream));
     OK(dev_alloc(&h->d_seed_pq, static_cast<size_t>(h->cg_grid)));
     OK(dev_alloc(&h->d_pq_parts, static_cast<size_t>(prop.multiProcessorCount)));
 #ifdef B200_WITH_NCCL
@@ -2137,7 +1999,7 @@ void b200_destroy(b200_handle* h) {
                       h->d_vp0, h->d_vp1, h->d_vr0, h->d_b, h->d_D, h->d_ete_inv, h->d_rhs, h->d_ye, h->d_upper45,
                       h->d_minv, h->d_blocks, h->d_xr, h->d_p, h->d_r, h->d_z, h->d_tmp, h->d_sol, h->d_cg,
                       h->d_scale, h->d_sqnorm, h->d_diagonal, h->d_lmD, h->d_step, h->d_cand, h->d_y, h->d_wtiles,
-                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_cams, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cg_bar, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_cb_chunks, h->d_cb_cta, h->d_cb_segs, h->d_cb_slots, h->d_pt_perm, h->d_row_perm, h->d_stage_p, h->d_stage_r,
+                      h->d_row_meta, h->d_cta_part, h->d_cta_cam, h->d_cta_cams, h->d_cta_big, h->d_cta_big_none, h->d_tile_meta, h->d_pq_parts, h->d_seed_pq, h->d_huge_pts, h->d_dense_s, h->d_dense_work, h->d_dense_info, h->d_ftf_inv, h->d_spse[0], h->d_spse[1], h->d_spse[2], h->d_partials, h->d_ybig, h->d_red, h->d_cam_items, h->d_cam_rows, h->d_q3, h->d_pt_perm, h->d_row_perm, h->d_stage_p, h->d_stage_r,
                       const_cast<TileDesc*>(h->view_big.tiles)};
   for (void* p : dev_ptrs)
     if (p != nullptr) cudaFree(p);

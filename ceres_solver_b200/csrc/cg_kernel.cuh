@@ -86,35 +86,7 @@ struct CgVecArgs {
   XchgPeers xg;                // xg.world == 0: single GPU / q already complete
   int xg_slot;
   unsigned xg_epoch;
-  int pdl;                     // launched as a programmatic dependent of the product: wait for it before touching q / p.q
-  unsigned* bar;               // {arrival count, generation}: grid barrier of an ORDINARY launch (all CTAs co-resident: the
-                               // grid is at most one CTA per SM and the stream holds nothing else while it runs); null: the
-                               // kernel was launched cooperatively and uses cooperative-groups grid.sync()
 };
-
-// Reusable grid-wide barrier for a grid whose CTAs are all resident (development A/B only: measured 3 % SLOWER per CG
-// iteration than the cooperative launch + grid.sync() it was meant to replace, so the product keeps the cooperative launch).
-// A wait that lasts longer than ~2 s traps (a barrier that can never complete must not hang the GPU).
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned* vgen = bar + 1;
-    const unsigned g = *vgen;            // generation, read BEFORE arriving
-    __threadfence();                     // release: this CTA's writes are visible before its arrival
-    if (atomicAdd(bar, 1u) == nblocks - 1u) {
-      atomicExch(bar, 0u);               // last one in: reset the count, then open the next generation
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*vgen == g) {
-        if (clock64() - t0 > 4000000000LL) __trap();
-      }
-    }
-    __threadfence();                     // acquire
-  }
-  __syncthreads();
-}
 
 // Sums up to three values over the CTA with one barrier pair; results valid in every thread.
 __device__ __forceinline__ void cg_block_sum3(double& a, double& b, double& c, double (*scratch)[3]) {
@@ -157,10 +129,9 @@ __device__ __forceinline__ void cg_totals(const double* red, int nb, int slot0, 
 }
 
 __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
-  auto grid_sync = [&]() {
-    if (a.bar != nullptr) grid_barrier(a.bar, gridDim.x);
-    else cg::this_grid().sync();
-  };
+  cg::grid_group grid = cg::this_grid();
+  // (A/B on hardware, round 2: an ordinary launch with a grid barrier in global memory was 3 % slower per CG iteration than
+  //  this cooperative launch, and launching it as a programmatic dependent of the product bought nothing on top.)
   __shared__ double scratch[kCgThreads / 32][3];
   __shared__ double s_tot[4];
   __shared__ double s_r[kCgCamsPerCta * 9];
@@ -203,9 +174,6 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       for (int k = 0; k < 9; ++k) mrow[k] = m[k];
     }
   }
-  // Everything above is complete before the product of this iteration even started (the product waited for the previous
-  // vector kernel before it let this one launch); what follows is what the product wrote.
-  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (a.pq_parts != nullptr && (mode == CG_NORMAL || mode == CG_RESET_FIRST)) {
     const int warp = tid >> 5, lane = tid & 31;
     if (warp == 0) {
@@ -248,7 +216,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     }
     cg_block_sum3(acc, d1, d2, scratch);
     if (tid == 0) a.red[blockIdx.x * 4 + 0] = acc;
-    grid_sync();
+    grid.sync();
   }
 
   // ------------------------------------------------------------------ phase B
@@ -369,7 +337,7 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       a.red[blockIdx.x * 4 + 3] = accRho;
     }
   }
-  grid_sync();
+  grid.sync();
 
   // ------------------------------------------------------------------ phase C
   double tot[3];

@@ -725,9 +725,6 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1)
     const int n = c.sy_stride * v.replicas;
     for (int i = threadIdx.x; i < n; i += blockDim.x) c.sy()[i] = 0.0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    // from here on the vector kernel before this product is complete: the vector kernel AFTER it may be launched (it can
-    // only become resident as this grid's CTAs exit, and it waits for this grid before it reads q)
-    asm volatile("griddepcontrol.launch_dependents;");
     if (done_flag != nullptr && __ldcg(done_flag) != 0) {  // PCG already terminated: nothing to do but let the TMA land
       v4_drain(v, c, 0);
       return;

@@ -9,6 +9,30 @@
 
 namespace b200 {
 
+// (A + D^2)^-1 of a symmetric 3x3 through its Cholesky factor, like invert_sym3_llt (the reference's
+// selfadjointView<Upper>().llt().solve(I), implicit_schur_complement.cc:201-202), but with reciprocal square roots only:
+// three rsqrt instead of three sqrt + six divisions.  FP64 sqrt / division are ~25-instruction sequences on a pipe that
+// issues a warp instruction every ~4.5 cycles: ncu attributed a third of the first version of the init kernel to them.
+// rsqrt(double) is accurate to 1-2 ulp, so the result differs from the division form by O(1e-16) relative.
+__device__ __forceinline__ void invert_sym3_llt_rsqrt(const double m[6], double inv[6]) {
+  const double i00 = rsqrt(m[0]);                 // 1 / l00
+  const double l10 = m[1] * i00, l20 = m[2] * i00;
+  const double i11 = rsqrt(m[3] - l10 * l10);     // 1 / l11
+  const double l21 = (m[4] - l20 * l10) * i11;
+  const double i22 = rsqrt(m[5] - l20 * l20 - l21 * l21);
+  // L^-1 (lower)
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  // inv = L^-T L^-1
+  inv[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  inv[1] = i10 * i11 + i20 * i21;
+  inv[2] = i20 * i22;
+  inv[3] = i11 * i11 + i21 * i21;
+  inv[4] = i21 * i22;
+  inv[5] = i22 * i22;
+}
+
 struct InitV4Args {
   const double* b;   // [2N]
   const double* D;   // [3P+9C] or null
@@ -128,7 +152,7 @@ __device__ __forceinline__ void init_big_points_impl(const V2View& v, const BigS
       m[3] += d1 * d1;
       m[5] += d2 * d2;
       double inv[6];
-      invert_sym3_llt(m, inv);
+      invert_sym3_llt_rsqrt(m, inv);
       const double v0 = inv[0] * m[6] + inv[1] * m[7] + inv[2] * m[8];
       const double v1 = inv[1] * m[6] + inv[3] * m[7] + inv[4] * m[8];
       const double v2 = inv[2] * m[6] + inv[4] * m[7] + inv[5] * m[8];
@@ -247,7 +271,7 @@ __global__ void __launch_bounds__(kV4MaxThreads, 1) schur_init_v4_kernel(V2View 
       m[3] += d1 * d1;
       m[5] += d2 * d2;
       double inv[6];
-      invert_sym3_llt(m, inv);   // every lane of the point computes the same inverse (the FP64 pipe is idle anyway)
+      invert_sym3_llt_rsqrt(m, inv);   // every lane of the point computes the same inverse
       const double v0 = inv[0] * m[6] + inv[1] * m[7] + inv[2] * m[8];
       const double v1 = inv[1] * m[6] + inv[3] * m[7] + inv[4] * m[8];
       const double v2 = inv[2] * m[6] + inv[4] * m[7] + inv[5] * m[8];
@@ -333,7 +357,7 @@ template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 constexpr int kCamBlkRowBytes = 144 + 32;                 // F row + Q block (q00, q01, q11, pad)
-constexpr int kCamBlkDepth = 3;                           // buffers per warp: data of two steps in flight behind the one computed
+constexpr int kCamBlkDepth = 2;                           // buffers per warp: the next 32 rows land while 32 are computed
 constexpr int kCamBlkWarpBytes = kCamBlkDepth * 32 * kCamBlkRowBytes;
 constexpr int kCamBlkThreads = 128;
 
@@ -395,11 +419,14 @@ __device__ __forceinline__ void cam_block_flush(double (&m)[46], double* dst) {
     if (r5[k] != 0.0) red_add(dst + base + k, r5[k]);   // padding entries are exactly zero and never reach an index >= 45
 }
 
-// Camera-major block diagonal.  One warp walks a strided sequence of items (slices of one camera's row list) as ONE
-// continuous stream of 32-row steps: each lane copies ITS (gathered) row of step s+2 into the warp's shared-memory ring with
-// cp.async while the warp computes step s, and the row indices of step s+3 are already being fetched -- no load latency is
-// exposed, neither inside an item nor between items (ncu on the register version: 43 % long-scoreboard stalls at 8-12
-// resident warps).  The 45 packed entries stay in registers per lane and are reduced across the lanes when an item ends.
+// Camera-major block diagonal.  One warp per item (a slice of one camera's row list, the reference's transpose block
+// structure, block_sparse_matrix.cc:784-808); each lane copies ITS (gathered) row of the next 32 rows into the warp's
+// shared-memory buffer with cp.async while the warp computes on the previous 32; the 45 packed entries stay in registers per
+// lane and are reduced across the lanes when the item ends.  Measured on Ladybug-1723 (profiles/r02_*): 42 us, i.e. the
+// 117 MB it reads arrive at 2.9 TB/s -- the kernel is bound by the DRAM access pattern of 144-byte gathers, not by latency:
+// three other organisations were built and measured and lost (register-only 43 us; one continuous cp.async stream across
+// items with three buffers 48 us; CTA-local streaming of the rows with the regrouping by camera done in shared memory by
+// quarter-warps 64 us, FP64-issue-bound at 8 warps) and are not in the build.
 template <bool kSchur>
 __global__ void __launch_bounds__(kCamBlkThreads, 3)
     cam_blocks_v2_kernel(ProblemView p, int num_items, const CamItem* __restrict__ items, const int* __restrict__ cam_rows,
@@ -407,270 +434,80 @@ __global__ void __launch_bounds__(kCamBlkThreads, 3)
   extern __shared__ __align__(128) unsigned char cb_smem[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const int stride = gridDim.x * warps_per_block;
   unsigned char* wbuf = cb_smem + (threadIdx.x >> 5) * kCamBlkWarpBytes;
-  struct Cursor {
-    int item, iter, begin, end;
-  };
-  auto load_item = [&](Cursor& c) {
-    c.iter = 0;
-    if (c.item < num_items) {
-      const CamItem it = items[c.item];
-      c.begin = it.begin;
-      c.end = it.end;
-    } else {
-      c.begin = c.end = 0;
-    }
-  };
-  auto advance = [&](Cursor& c) {
-    ++c.iter;
-    if (c.begin + 32 * c.iter >= c.end) {
-      c.item += stride;
-      load_item(c);
-    }
-  };
-  auto row_of = [&](const Cursor& c) -> int {
-    const int j = c.begin + 32 * c.iter + lane;
-    return (c.item < num_items && j < c.end) ? __ldg(cam_rows + j) : -1;
-  };
-  auto issue = [&](int r, int buf) {
-    if (r >= 0) {
-      unsigned char* dst = wbuf + buf * 32 * kCamBlkRowBytes + lane * 144;
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.F() + 18 * static_cast<size_t>(r));
+  for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < num_items; item += gridDim.x * warps_per_block) {
+    const CamItem it = items[item];
+    double m[46];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) cp_async16(dst + 16 * k, src + 16 * k);
-      if (kSchur) {
-        unsigned char* dq = wbuf + buf * 32 * kCamBlkRowBytes + 32 * 144 + lane * 32;
-        const double* sq = q3 + kQStride * static_cast<size_t>(r);
-        cp_async16(dq, sq);
-        cp_async16(dq + 16, sq + 2);
-      }
-    }
-    cp_async_commit();
-  };
-  Cursor cp, ix;
-  cp.item = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  load_item(cp);
-  ix = cp;
-  int r_cur = row_of(ix);
-  advance(ix);
-  int r_nxt = row_of(ix);
-  advance(ix);
-  int r_pend = row_of(ix);
-  advance(ix);
-  issue(r_cur, 0);
-  issue(r_nxt, 1);
-  double m[46];
+    for (int k = 0; k < 46; ++k) m[k] = 0.0;
+    const int iters = (it.end - it.begin + 31) >> 5;
+    auto row_of = [&](int iter) -> int {
+      const int j = it.begin + 32 * iter + lane;
+      return (iter < iters && j < it.end) ? __ldg(cam_rows + j) : -1;
+    };
+    // Two adjacent lanes fetch ONE row together, 32 bytes per step: a row is 144 B = 4.5 sectors, and with each lane on its
+    // own row every 16-byte cp.async was a separate half-empty sector request to L2 (11 requests per row, counting Q);
+    // paired on sector boundaries it takes 6 (rows start at 144 r: the pairs of row r begin at chunk r & 1).
+    auto issue = [&](int r, int buf) {
+      unsigned char* fbuf = wbuf + buf * 32 * kCamBlkRowBytes;
 #pragma unroll
-  for (int k = 0; k < 46; ++k) m[k] = 0.0;
-  int stage = 0;
-  while (cp.item < num_items) {
-    const int r_far = row_of(ix);   // row indices three steps ahead: their latency hides behind this step
-    advance(ix);
-    issue(r_pend, stage == 0 ? 2 : stage - 1);   // data two steps ahead
-    cp_async_wait<2>();
-    __syncwarp();
-    if (r_cur >= 0) {
-      const double* fr = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + lane * 144);
-      double f[18];
+      for (int half = 0; half < 2; ++half) {
+        const int slot = 16 * half + (lane >> 1);                    // row slot served by this lane pair
+        const int rr = __shfl_sync(0xffffffffu, r, slot);             // its row (held by lane `slot`)
+        if (rr >= 0) {
+          const unsigned char* src = reinterpret_cast<const unsigned char*>(p.F() + 18 * static_cast<size_t>(rr));
+          unsigned char* dst = fbuf + slot * 144;
+          const int first = (lane & 1) - (rr & 1);                   // chunk of this lane in step 0: -1, 0 or 1
 #pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const double2 w = lds2(fr + 2 * k);
-        f[2 * k] = w.x;
-        f[2 * k + 1] = w.y;
-      }
-      double q00 = 1.0, q01 = 0.0, q11 = 1.0;
-      if (kSchur) {
-        const double* q = reinterpret_cast<const double*>(wbuf + stage * 32 * kCamBlkRowBytes + 32 * 144 + lane * 32);
-        q00 = q[0];
-        q01 = q[1];
-        q11 = q[2];
-      }
-      int idx = 0;
-#pragma unroll
-      for (int aa = 0; aa < 9; ++aa) {
-        const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
-#pragma unroll
-        for (int bb = aa; bb < 9; ++bb) {
-          m[idx] += ga * f[bb] + gb * f[9 + bb];
-          ++idx;
+          for (int c = 0; c < 5; ++c) {
+            const int chunk = 2 * c + first;
+            if (chunk >= 0 && chunk <= 8) cp_async16(dst + 16 * chunk, src + 16 * chunk);
+          }
+          if (kSchur) cp_async16(fbuf + 32 * 144 + slot * 32 + 16 * (lane & 1), q3 + kQStride * static_cast<size_t>(rr) + 2 * (lane & 1));
         }
       }
-    }
-    if (cp.begin + 32 * (cp.iter + 1) >= cp.end) {   // last step of the item (uniform over the warp)
-      cam_block_flush(m, out45 + 45 * static_cast<size_t>(items[cp.item].cam));
+      cp_async_commit();
+    };
+    int r_cur = row_of(0), r_nxt = row_of(1);
+    issue(r_cur, 0);
+    for (int i = 0; i < iters; ++i) {
+      const int r_nn = row_of(i + 2);
+      issue(r_nxt, (i + 1) & 1);
+      cp_async_wait<1>();
+      __syncwarp();
+      if (r_cur >= 0) {
+        const double* fr = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + lane * 144);
+        double f[18];
 #pragma unroll
-      for (int k = 0; k < 46; ++k) m[k] = 0.0;
-    }
-    __syncwarp();   // the buffer is refilled by the issue of the next step
-    advance(cp);
-    r_cur = r_nxt;
-    r_nxt = r_pend;
-    r_pend = r_far;
-    stage = stage == 2 ? 0 : stage + 1;
-  }
-  cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------------
-// Camera-major block diagonal, CTA-local (third version).  The gather version above reads every F row exactly once but in
-// camera-major order, i.e. as 144-byte pieces scattered over the whole array: measured 2.9 TB/s at best, whatever the
-// latency hiding (register, cp.async double buffer, continuous stream: 42-48 us on Ladybug-1723).  Here every persistent CTA
-// STREAMS its own contiguous row range (the same partition as the warp-tile kernels) through shared memory in chunks of up to
-// 512 rows -- two bulk copies per chunk, DRAM sees a linear read -- and the regrouping by camera happens on chip: the host
-// sorted the rows of every chunk by camera once (b200_create), a quarter-warp takes one (camera, chunk) segment, its eight
-// lanes walk the segment's rows in shared memory with the 45 packed entries in registers, reduce them by recursive halving
-// over the eight lanes and add the result to the CTA's private accumulator of that camera (plain read-modify-write: a
-// segment has exactly one owner and chunks are separated by a CTA barrier).  One flush of <= span x 45 REDs per CTA.
-// ------------------------------------------------------------------------------------------------
-struct CbChunk {
-  int row_begin, row_count;   // rows of the chunk (<= kCbChunkRows)
-  int seg_begin, seg_count;   // its (camera, chunk) segments in CbView::segs, longest first (<= kCbMaxSegs)
-  int slot_begin;             // its sorted row slots in CbView::slots (multiple of 8)
-  int pad0, pad1, pad2;
-};
-struct CbView {
-  const CbChunk* chunks;
-  const int2* cta_chunks;     // per CTA: [begin, end) into chunks
-  const uint2* segs;          // x = camera position in the CTA's list | rows << 16 ; y = offset into the chunk's slot list
-  const unsigned short* slots;
-};
-constexpr int kCbChunkRows = 512;
-constexpr int kCbMaxSegs = 128;
-constexpr int kCbThreads = 256;
-constexpr int kCbBufBytes = kCbChunkRows * 144 + kCbChunkRows * 32 + kCbMaxSegs * 8 + kCbChunkRows * 2;
-__host__ __device__ inline size_t cb3_acc_bytes(int max_cam_span) { return (static_cast<size_t>(45) * max_cam_span * 8 + 127) & ~static_cast<size_t>(127); }
-__host__ __device__ inline size_t cb3_smem_bytes(int max_cam_span) { return cb3_acc_bytes(max_cam_span) + 2 * kCbBufBytes + 64; }
-
-template <bool kSchur>
-__global__ void __launch_bounds__(kCbThreads, 1)
-    cam_blocks_v3_kernel(V2View v, CbView cb, const double* __restrict__ q3, double* out45) {
-  extern __shared__ __align__(128) unsigned char cb_smem[];
-  double* sacc = reinterpret_cast<double*>(cb_smem);
-  unsigned char* bufs = cb_smem + cb3_acc_bytes(v.max_cam_span);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(bufs + 2 * kCbBufBytes);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int2 cr = v.cta_cam[blockIdx.x];
-  const int2 cc = cb.cta_chunks[blockIdx.x];
-  const int nacc = 45 * v2_span(v, cr);
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) sacc[i] = 0.0;
-  if (threadIdx.x == 0) {
-    mbar_init(bars, 1);
-    mbar_init(bars + 1, 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-  auto issue = [&](int k) {   // thread 0: chunk k of this CTA -> buffer k & 1
-    const CbChunk ch = cb.chunks[cc.x + k];
-    unsigned char* buf = bufs + (k & 1) * kCbBufBytes;
-    uint64_t* bar = bars + (k & 1);
-    const uint32_t fb = ch.row_count * 144u, qb = kSchur ? ch.row_count * 32u : 0u;
-    const uint32_t sb = ((ch.seg_count * 8u) + 15u) & ~15u, lb = ((ch.row_count * 2u) + 15u) & ~15u;
-    mbar_arrive_expect_tx(bar, fb + qb + sb + lb);
-    bulk_g2s(buf, v.p.F() + 18 * static_cast<size_t>(ch.row_begin), fb, bar);
-    if (kSchur) bulk_g2s(buf + kCbChunkRows * 144, q3 + kQStride * static_cast<size_t>(ch.row_begin), qb, bar);
-    bulk_g2s(buf + kCbChunkRows * 176, cb.segs + ch.seg_begin, sb, bar);
-    bulk_g2s(buf + kCbChunkRows * 176 + kCbMaxSegs * 8, cb.slots + ch.slot_begin, lb, bar);
-  };
-  const int nchunks = cc.y - cc.x;
-  if (threadIdx.x == 0) {
-    if (nchunks > 0) issue(0);
-    if (nchunks > 1) issue(1);
-  }
-  const int quarter = lane >> 3, sub = lane & 7;
-  const int base = ((lane & 4) ? 24 : 0) + ((lane & 2) ? 12 : 0) + ((lane & 1) ? 6 : 0);
-  for (int k = 0; k < nchunks; ++k) {
-    const int seg_count = cb.chunks[cc.x + k].seg_count;   // (L2 hit; in flight while the chunk lands)
-    const unsigned char* buf = bufs + (k & 1) * kCbBufBytes;
-    const double* sF = reinterpret_cast<const double*>(buf);
-    const double* sQ = reinterpret_cast<const double*>(buf + kCbChunkRows * 144);
-    const uint2* sSeg = reinterpret_cast<const uint2*>(buf + kCbChunkRows * 176);
-    const unsigned short* sSlot = reinterpret_cast<const unsigned short*>(buf + kCbChunkRows * 176 + kCbMaxSegs * 8);
-    mbar_wait(bars + (k & 1), (k >> 1) & 1);
-    for (int s0 = 0; s0 < seg_count; s0 += 4 * (kCbThreads / 32)) {
-      const int sidx = s0 + warp * 4 + quarter;
-      int cam_l = 0, count = 0, slot0 = 0;
-      if (sidx < seg_count) {
-        const uint2 sg = sSeg[sidx];
-        cam_l = static_cast<int>(sg.x & 0xffffu);
-        count = static_cast<int>(sg.x >> 16);
-        slot0 = static_cast<int>(sg.y);
-      }
-      int cmax = count;
+        for (int k = 0; k < 9; ++k) {
+          const double2 w = lds2(fr + 2 * k);
+          f[2 * k] = w.x;
+          f[2 * k + 1] = w.y;
+        }
+        double q00 = 1.0, q01 = 0.0, q11 = 1.0;
+        if (kSchur) {
+          const double* q = reinterpret_cast<const double*>(wbuf + (i & 1) * 32 * kCamBlkRowBytes + 32 * 144 + lane * 32);
+          q00 = q[0];
+          q01 = q[1];
+          q11 = q[2];
+        }
+        int idx = 0;
 #pragma unroll
-      for (int o = 16; o >= 8; o >>= 1) cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-      double m[48];
+        for (int aa = 0; aa < 9; ++aa) {
+          const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
 #pragma unroll
-      for (int q = 0; q < 48; ++q) m[q] = 0.0;
-      for (int i = sub; i < cmax; i += 8) {
-        if (i < count) {
-          const int slot = sSlot[slot0 + i];
-          const double* fr = sF + slot * 18;
-          double f[18];
-#pragma unroll
-          for (int q = 0; q < 9; ++q) {
-            const double2 w = lds2(fr + 2 * q);
-            f[2 * q] = w.x;
-            f[2 * q + 1] = w.y;
-          }
-          double q00 = 1.0, q01 = 0.0, q11 = 1.0;
-          if (kSchur) {
-            const double2 qa = lds2(sQ + slot * 4), qb2 = lds2(sQ + slot * 4 + 2);
-            q00 = qa.x;
-            q01 = qa.y;
-            q11 = qb2.x;
-          }
-          int idx = 0;
-#pragma unroll
-          for (int aa = 0; aa < 9; ++aa) {
-            const double ga = q00 * f[aa] + q01 * f[9 + aa], gb = q01 * f[aa] + q11 * f[9 + aa];   // row aa of F'Q
-#pragma unroll
-            for (int bb = aa; bb < 9; ++bb) {
-              m[idx] += ga * f[bb] + gb * f[9 + bb];
-              ++idx;
-            }
+          for (int bb = aa; bb < 9; ++bb) {
+            m[idx] += ga * f[bb] + gb * f[9 + bb];
+            ++idx;
           }
         }
       }
-      // recursive halving over the eight lanes of the quarter: 48 -> 24 -> 12 -> 6 entries per lane
-      double r1[24], r2[12], r3[6];
-      {
-        const bool up = (lane & 4) != 0;
-#pragma unroll
-        for (int q = 0; q < 24; ++q) {
-          const double keep = up ? m[24 + q] : m[q], give = up ? m[q] : m[24 + q];
-          r1[q] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
-        }
-      }
-      {
-        const bool up = (lane & 2) != 0;
-#pragma unroll
-        for (int q = 0; q < 12; ++q) {
-          const double keep = up ? r1[12 + q] : r1[q], give = up ? r1[q] : r1[12 + q];
-          r2[q] = keep + __shfl_xor_sync(0xffffffffu, give, 2);
-        }
-      }
-      {
-        const bool up = (lane & 1) != 0;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) {
-          const double keep = up ? r2[6 + q] : r2[q], give = up ? r2[q] : r2[6 + q];
-          r3[q] = keep + __shfl_xor_sync(0xffffffffu, give, 1);
-        }
-      }
-      if (sidx < seg_count) {
-        double* acc = sacc + 45 * cam_l + base;
-#pragma unroll
-        for (int q = 0; q < 6; ++q)
-          if (base + q < 45) acc[q] += r3[q];
-      }
+      __syncwarp();   // the buffer is refilled two iterations later
+      r_cur = r_nxt;
+      r_nxt = r_nn;
     }
-    __syncthreads();   // every warp is done with the buffer (and with this chunk's accumulator updates)
-    if (threadIdx.x == 0 && k + 2 < nchunks) issue(k + 2);
-  }
-  for (int i = threadIdx.x; i < nacc; i += blockDim.x) {
-    const double acc = sacc[i];
-    if (acc != 0.0) red_add(out45 + v2_global_entry(v, cr, i, 45), acc);
+    cp_async_wait<0>();
+    cam_block_flush(m, out45 + 45 * static_cast<size_t>(it.cam));
   }
 }
 

@@ -102,7 +102,7 @@ def test_first_lm_iterations_match_oracle(case, oracle_traces, host_boundary):
     accept/reject sequence; cost, step norm, gradient norm and radius to north_star's 1e-6 -- or, where the oracle itself
     cannot reproduce its own numbers to 1e-6 under a change of summation order, measured against the oracle's own spread
     (tests/conftest.py: compare_lm_traces)."""
-    from conftest import compare_lm_traces
+    from tests.conftest import compare_lm_traces
     recs_o, recs_o2 = oracle_traces
     _, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(max_num_iterations=3), host_boundary=host_boundary)
     assert len(recs) == 4

@@ -150,7 +150,7 @@ def oracle_traces(case):
 
 @pytest.mark.parametrize("host_boundary", [False, True])
 def test_lm_trajectory(case, oracle_traces, host_boundary):
-    from conftest import compare_lm_traces
+    from tests.conftest import compare_lm_traces
     (state_o, recs_o), (state_o2, recs_o2) = oracle_traces
     state, recs = case.gpu.lm_solve(case.state, case.gpu.lm_options(max_num_iterations=4), host_boundary=host_boundary)
     compare_lm_traces(recs, recs_o, recs_o2, keys=("cost", "step_norm"))
