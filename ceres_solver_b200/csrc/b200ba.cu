@@ -764,7 +764,7 @@ int schur_solve_dev(b200_handle* h, const double* d_b, const double* d_D, const 
     });
   };
   // p.q fused into the product's flush (single GPU, v4 kernel, direct flush, no separate big-point launch)
-  const bool fuse_pq = seeded && h->mul_v4 && h->world == 1 && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
+  const bool fuse_pq = seeded && h->mul_v4 && (h->world == 1 || xchg) && h->num_huge == 0 && (h->num_big_tiles == 0 || h->big_folded) &&
                        dev_env("B200_NO_FUSED_PQ") == nullptr;
   double* pq_parts = fuse_pq ? h->d_pq_parts : nullptr;
   va.pq_parts = pq_parts;
@@ -1913,8 +1913,8 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
       // communicator (the only plumbing the ranks share), every peer's buffer mapped into this process.  Any failure
       // (no P2P path, IPC unavailable in the launch mode) leaves the NCCL all-reduce in place -- decided jointly.
       const size_t nC = 9 * static_cast<size_t>(C);
-      OK(dev_alloc(&h->d_xchg, 2 * static_cast<size_t>(h->world) * nC));
-      CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(uint4) * 2 * h->world * nC, h->stream));   // epoch 0 is never used
+      OK(dev_alloc(&h->d_xchg, 2 * static_cast<size_t>(h->world) * (nC + 1)));
+      CU(cudaMemsetAsync(h->d_xchg, 0, sizeof(uint4) * 2 * h->world * (nC + 1), h->stream));   // epoch 0 is never used
       unsigned char* d_handles = nullptr;
       OK(dev_alloc(&d_handles, static_cast<size_t>(h->world) * 64));
       std::vector<unsigned char> hh(static_cast<size_t>(h->world) * 64, 0);

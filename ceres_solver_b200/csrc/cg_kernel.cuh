@@ -28,7 +28,7 @@ enum CgMode { CG_NORMAL = 0, CG_RESET_FIRST = 1, CG_RESET_SECOND = 2, CG_BEGIN =
 
 constexpr int kMaxXchgRanks = 8;
 struct XchgPeers {
-  uint4* buf[kMaxXchgRanks];   // every rank's exchange buffer [2 slots][world][9C] packets, as mapped into THIS process
+  uint4* buf[kMaxXchgRanks];   // every rank's exchange buffer [2 slots][world][9C + 1] packets, as mapped into THIS process
   int world, rank;
 };
 
@@ -47,6 +47,7 @@ __device__ __forceinline__ double xchg_wait_load(const uint4* src, unsigned epoc
   return __hiloint2double(static_cast<int>(c), static_cast<int>(a));
 }
 // this rank's partial v of entry j -> every peer; returns the rank-ordered sum over all ranks' partials of entry j
+// (n: packets per rank and slot = 9C entries of q + 1 for the scalar p.q partial)
 __device__ __forceinline__ double xchg_allsum(const XchgPeers& xg, int slot, unsigned epoch, int n, int j, double v) {
   const size_t base = static_cast<size_t>(slot) * xg.world * n;
 #pragma unroll
@@ -189,13 +190,13 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
     // exchange + rank-ordered sum of the partial products (replaces qj / a.q)
     if (single) {
       if (ok0) {
-        qj = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n, j0, __ldcg(a.q + j0));
+        qj = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n + 1, j0, __ldcg(a.q + j0));
         a.q[j0] = qj;
       }
     } else {
       for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int j = blk * kCgCamsPerCta * 9 + tid;
-        if (lane_ok && j < n) a.q[j] = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n, j, __ldcg(a.q + j));
+        if (lane_ok && j < n) a.q[j] = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n + 1, j, __ldcg(a.q + j));
       }
     }
   }
@@ -235,6 +236,14 @@ __global__ void __launch_bounds__(kCgThreads) cg_vector_kernel(CgVecArgs a) {
       }
       __syncthreads();
       pq = s_tot[0] + s_tot[1];
+      if (a.xg.world > 1) {
+        // sharded: that was this rank's share of p.q (its partial product dotted with p; the D_f^2 term lives on rank 0);
+        // the ranks' shares travel as one more packet (index n) and are summed in rank order like the entries of q
+        __syncthreads();
+        if (tid == 0) s_tot[2] = xchg_allsum(a.xg, a.xg_slot, a.xg_epoch, n + 1, n, pq);
+        __syncthreads();
+        pq = s_tot[2];
+      }
     } else {
       cg_totals(a.red, gridDim.x, 0, 1, &pq, s_tot);
     }
