@@ -1968,7 +1968,7 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   const double Nn = N, Pp = P, Cc = C;
   h->bytes_per_op[K_JTJ] = 196 * Nn + 4 * Pp + 24.0 * (3 * Pp + 9 * Cc);
   h->bytes_per_op[K_SCHUR_MUL] = 196 * Nn + 52 * Pp + 216 * Cc;
-  h->bytes_per_op[K_SCHUR_INIT] = 196 * Nn + 16 * Nn + 4 * Pp + 24 * Pp + 48 * Pp + 24 * Pp + 72 * Cc;
+  h->bytes_per_op[K_SCHUR_INIT] = 196 * Nn + 16 * Nn + 4 * Pp + 24 * Pp + 48 * Pp + 72 * Cc;   // J, b, chunk ids, D_e, (E'E)^-1 out, rhs out
   h->bytes_per_op[K_DIAG_BLOCKS] = 196 * Nn + 52 * Pp + 360 * Cc;
   h->bytes_per_op[K_BACKSUB] = 196 * Nn + 16 * Nn + 52 * Pp + 24 * Pp + 72 * Cc;
   h->bytes_per_op[K_EVAL_JAC] = 192 * Nn + 16 * Nn + 16 * Nn + 4 * Nn + 4 * Pp + 2 * 8.0 * (3 * Pp + 9 * Cc);
@@ -2598,7 +2598,8 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     if (rc == B200_ERR_EVALUATION_FAILED) candidate_cost = std::numeric_limits<double>::max();
     else if (rc != B200_OK) return rc;
 
-    it.step_norm = std::sqrt(step_sq);
+    // (assigned only once a step has been accepted, like the reference: trust_region_minimizer.cc:113, :730)
+    it.step_norm = at_least_one_successful ? std::sqrt(step_sq) : 0.0;
     if (at_least_one_successful && it.step_norm <= opt->parameter_tolerance * (std::sqrt(x_sq) + opt->parameter_tolerance)) break;
     it.cost_change = x_cost - candidate_cost;
     if (std::fabs(it.cost_change) <= opt->function_tolerance * x_cost) break;

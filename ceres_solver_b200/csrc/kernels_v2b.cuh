@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
   __syncthreads();
   double* my_g = sg_acc + (warp % v.replicas) * rstride;
   double* my_q = sq_acc + (warp % v.replicas) * rstride;
+  const bool owned = v.replicas >= static_cast<int>(blockDim.x >> 5);   // (uniform) no other warp touches this warp's copies
   const size_t camoff = 3 * static_cast<size_t>(v.p.P);
   double cost = 0.0;
   bool store_pending = false;
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
         a.gradient[po + 1] = gps[1];
         a.gradient[po + 2] = gps[2];
       }
-      cam_accumulate<9>(my_g, cam_l, active, gc);
+      if (owned) cam_accumulate9_owned(my_g, cam_l, active, gc);   // one private copy per warp: plain read-modify-write
+      else cam_accumulate<9>(my_g, cam_l, active, gc);
     }
     if (a.scale != nullptr && active) {
       const double* sc = a.scale + camoff + 9 * static_cast<size_t>(cam);
@@ -240,7 +242,8 @@ __global__ void __launch_bounds__(kV2MaxThreads, 1) evaluate_v2_kernel(V2View v,
         a.sqnorm[po + 1] = qps[1];
         a.sqnorm[po + 2] = qps[2];
       }
-      cam_accumulate<9>(my_q, cam_l, active, qc);
+      if (owned) cam_accumulate9_owned(my_q, cam_l, active, qc);
+      else cam_accumulate<9>(my_q, cam_l, active, qc);
     }
     // Jacobian cells: stage the warp's rows contiguously, then one TMA bulk store each for E and F
     if (store_pending) {

