@@ -74,7 +74,7 @@ class KernelStat(C.Structure):
 
 # Every symbol include/b200ba.h declares (tests/test_abi.py checks the library exports all of them).
 SYMBOLS = [
-    "b200_nccl_unique_id", "b200_create", "b200_destroy", "b200_last_error", "b200_num_parameters",
+    "b200_plan_point_order", "b200_nccl_unique_id", "b200_create", "b200_destroy", "b200_last_error", "b200_num_parameters",
     "b200_num_residuals", "b200_evaluate", "b200_set_apply_loss_function", "b200_plus", "b200_jacobian_squared_column_norm",
     "b200_jacobian_scale_columns", "b200_jacobian_right_multiply", "b200_jacobian_left_multiply", "b200_model_cost_change",
     "b200_jacobian_get_values", "b200_jacobian_set_values", "b200_partitioned_multiply", "b200_jtj_multiply", "b200_solver_options_default",
@@ -112,6 +112,21 @@ def _f64(a):
 def _check(rc):
     if rc != OK:
         raise B200Error(rc, lib().b200_last_error().decode())
+
+
+def plan_point_order(num_cameras, num_points, cam_idx, pt_idx, num_chunks=148):
+    """Host-only: the internal point order b200_create would choose.  Returns (perm, metrics[4], choice)."""
+    cam = np.ascontiguousarray(cam_idx, dtype=np.int32)
+    pt = np.ascontiguousarray(pt_idx, dtype=np.int32)
+    d = BaDesc()
+    d.num_cameras, d.num_points, d.num_observations = int(num_cameras), int(num_points), len(cam)
+    d.cam_idx = cam.ctypes.data_as(_ip)
+    d.pt_idx = pt.ctypes.data_as(_ip)
+    perm = np.zeros(int(num_points), dtype=np.int32)
+    metrics = (C.c_int64 * 4)()
+    choice = C.c_int()
+    _check(lib().b200_plan_point_order(C.byref(d), int(num_chunks), perm.ctypes.data_as(_ip), metrics, C.byref(choice)))
+    return perm, [int(m) for m in metrics], choice.value
 
 
 def nccl_unique_id():

@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <numeric>
 #include <string>
 #include <vector>
 
@@ -1129,6 +1130,88 @@ int sharded_reduce(b200_handle* h, int grid, int slots, unsigned op_mask, double
   return B200_OK;
 }
 
+// ---- Internal point order.  The fast kernels give every persistent CTA a contiguous run of points and keep the cameras
+// those points see in shared memory, so they want neighbouring points to see the same few cameras.  The caller's e-block
+// order is whatever Ceres' ordering produced (first use in the residual list); the library is free to keep its own: points
+// (with all their rows, in the caller's relative order) are re-ordered privately, and every vector / matrix that crosses the
+// ABI is permuted at the boundary (up_* / down_*), so the layout contract of the header (block_jacobian_writer.cc:68-167,
+// reorder_program.cc:262-273) is untouched.  Candidates: 0 the caller's order; 1 by the start of the point's camera ARC (its
+// cameras seen as a set on the circle of camera ids, the arc being the complement of the largest gap: the smallest camera
+// unless the set wraps around -- keeps the seam of a loop closure together), then the arc's length; 2 by mean camera id; 3 by
+// smallest, then largest camera id.  Score: distinct cameras per 1/chunks-th of the rows, summed; the best wins, the caller's
+// order whenever it is within 10 % of the best (no boundary permutation then).  Pure host code (tests/test_host.py).
+const char* const kOrderNames[4] = {"caller's order kept", "by camera arc", "by mean camera", "by smallest camera"};
+int choose_point_order(int C, int P, int N, const int32_t* cam_of_row, const int* caller_ptr, int chunks, std::vector<int>* perm,
+                       long metrics[4]) {
+  std::vector<int> ident(static_cast<size_t>(P));
+  std::iota(ident.begin(), ident.end(), 0);
+  auto metric = [&](const std::vector<int>& ord) -> long {
+    std::vector<int> stamp(static_cast<size_t>(C), -1);
+    long total = 0, rows = 0;
+    int chunk = 0;
+    const long target = N / chunks + 1;
+    for (int k = 0; k < P; ++k) {
+      const int q = ord[k];
+      for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
+        const int c = cam_of_row[r];
+        if (stamp[c] != chunk) {
+          stamp[c] = chunk;
+          ++total;
+        }
+      }
+      rows += caller_ptr[q + 1] - caller_ptr[q];
+      while (rows >= static_cast<long>(chunk + 1) * target) ++chunk;
+    }
+    return total;
+  };
+  std::vector<long long> key[3];
+  for (auto& k : key) k.resize(static_cast<size_t>(P));
+  {
+    std::vector<int> cams;
+    for (int q = 0; q < P; ++q) {
+      const int deg = caller_ptr[q + 1] - caller_ptr[q];
+      long long sum = 0;
+      cams.clear();
+      for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
+        cams.push_back(cam_of_row[r]);
+        sum += cam_of_row[r];
+      }
+      std::sort(cams.begin(), cams.end());
+      long long start = C, len = 0, lo = C, hi = C;
+      if (deg > 0) {
+        int best_gap = cams[0] + C - cams[deg - 1];   // the gap that wraps around
+        start = cams[0];
+        for (int i = 1; i < deg; ++i)
+          if (cams[i] - cams[i - 1] > best_gap) {
+            best_gap = cams[i] - cams[i - 1];
+            start = cams[i];
+          }
+        len = C - best_gap;
+        lo = cams[0];
+        hi = cams[deg - 1];
+      }
+      key[0][q] = start * (static_cast<long long>(C) + 1) + len;
+      key[1][q] = deg > 0 ? (sum * 64) / deg : static_cast<long long>(C) * 64;
+      key[2][q] = lo * (static_cast<long long>(C) + 1) + hi;
+    }
+  }
+  metrics[0] = metric(ident);
+  std::vector<int> cand[3];
+  int best = 0;
+  for (int c = 0; c < 3; ++c) {
+    cand[c] = ident;
+    std::stable_sort(cand[c].begin(), cand[c].end(), [&](int a, int b) { return key[c][a] < key[c][b]; });
+    metrics[c + 1] = metric(cand[c]);
+    if (metrics[c + 1] < metrics[best + 1]) best = c;
+  }
+  if (static_cast<double>(metrics[0]) > 1.10 * static_cast<double>(metrics[best + 1])) {
+    *perm = cand[best];
+    return best + 1;
+  }
+  *perm = ident;
+  return 0;
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -1149,6 +1232,31 @@ int b200_nccl_unique_id(void* out128) {
   (void)out128;
   return fail(B200_ERR_UNSUPPORTED, "built without NCCL");
 #endif
+}
+
+int b200_plan_point_order(const b200_ba_desc* desc, int num_chunks, int32_t* perm_out, int64_t metrics_out[4], int* choice_out) {
+  if (desc == nullptr || desc->cam_idx == nullptr || desc->pt_idx == nullptr || num_chunks < 1)
+    return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
+  const int C = desc->num_cameras, P = desc->num_points;
+  const int N = static_cast<int>(desc->num_observations);
+  if (C <= 0 || P <= 0 || N <= 0) return fail(B200_ERR_INVALID_ARGUMENT, "empty problem");
+  std::vector<int> ptr(static_cast<size_t>(P) + 1, 0);
+  for (int i = 0; i < N; ++i) {
+    const int pt = desc->pt_idx[i], cam = desc->cam_idx[i];
+    if (pt < 0 || pt >= P || cam < 0 || cam >= C) return fail(B200_ERR_INVALID_ARGUMENT, "row %d: block id out of range", i);
+    if (i > 0 && pt < desc->pt_idx[i - 1]) return fail(B200_ERR_INVALID_ARGUMENT, "rows are not grouped by e block at row %d", i);
+    ptr[pt + 1]++;
+  }
+  for (int k = 0; k < P; ++k) ptr[k + 1] += ptr[k];
+  std::vector<int> perm;
+  long m[4];
+  const int choice = choose_point_order(C, P, N, desc->cam_idx, ptr.data(), num_chunks, &perm, m);
+  if (perm_out != nullptr)
+    for (int k = 0; k < P; ++k) perm_out[k] = perm[k];
+  if (metrics_out != nullptr)
+    for (int k = 0; k < 4; ++k) metrics_out[k] = m[k];
+  if (choice_out != nullptr) *choice_out = choice;
+  return B200_OK;
 }
 
 void b200_solver_options_default(b200_solver_options* o) {
@@ -1215,83 +1323,16 @@ int b200_create(const b200_ba_desc* desc, b200_handle** out) {
   }
   for (int k = 0; k < P; ++k) caller_ptr[k + 1] += caller_ptr[k];
 
-  // ---- Internal point order.  The fast kernels give every persistent CTA a contiguous run of points and keep the
-  // cameras those points see in shared memory, so they want neighbouring points to see the same few cameras.  The caller's
-  // e-block order is whatever Ceres' ordering produced (first use in the residual list); the library is free to keep its
-  // own: points (with all their rows, in the caller's relative order) are re-ordered privately here, and every vector /
-  // matrix that crosses the ABI is permuted at the boundary (up_* / down_* below), so the layout contract of the header
-  // (block_jacobian_writer.cc:68-167, reorder_program.cc:262-273) is untouched.  Candidates: the caller's order, by
-  // the start of the point's camera arc, by mean camera id; the one with the fewest distinct cameras per 1/num_SM-th of the rows wins, the
-  // caller's order when it is within 10 % of the best (no boundary permutation then).
-  std::vector<int> pt_perm(static_cast<size_t>(P));   // internal point k = caller point pt_perm[k]
-  bool identity_order = true;
-  {
-    for (int k = 0; k < P; ++k) pt_perm[k] = k;
-    const int chunks = prop.multiProcessorCount;
-    auto metric = [&](const std::vector<int>& ord) -> long {
-      std::vector<int> stamp(static_cast<size_t>(C), -1);
-      long total = 0, rows = 0;
-      int chunk = 0;
-      const long target = N / chunks + 1;
-      for (int k = 0; k < P; ++k) {
-        const int q = ord[k];
-        for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
-          const int c = desc->cam_idx[r];
-          if (stamp[c] != chunk) {
-            stamp[c] = chunk;
-            ++total;
-          }
-        }
-        rows += caller_ptr[q + 1] - caller_ptr[q];
-        while (rows >= static_cast<long>(chunk + 1) * target) ++chunk;
-      }
-      return total;
-    };
-    const long m_id = metric(pt_perm);
-    // keys: (a) start of the point's camera ARC -- its cameras seen as a set on the circle of camera ids, the arc being the
-    // complement of the largest gap; for sets that do not wrap around this is the smallest camera id, for captures whose
-    // last frames look at what the first ones saw (loops) it keeps the points of the seam together -- then the arc's
-    // length; (b) the mean camera id.
-    std::vector<long long> karc(static_cast<size_t>(P)), kmean(static_cast<size_t>(P));
-    {
-      std::vector<int> cams;
-      for (int q = 0; q < P; ++q) {
-        const int deg = caller_ptr[q + 1] - caller_ptr[q];
-        long long sum = 0;
-        cams.clear();
-        for (int r = caller_ptr[q]; r < caller_ptr[q + 1]; ++r) {
-          cams.push_back(desc->cam_idx[r]);
-          sum += desc->cam_idx[r];
-        }
-        std::sort(cams.begin(), cams.end());
-        long long start = C, len = 0;
-        if (deg > 0) {
-          int best_gap = cams[0] + C - cams[deg - 1];   // the gap that wraps around
-          start = cams[0];
-          for (int i = 1; i < deg; ++i)
-            if (cams[i] - cams[i - 1] > best_gap) {
-              best_gap = cams[i] - cams[i - 1];
-              start = cams[i];
-            }
-          len = C - best_gap;
-        }
-        karc[q] = start * (static_cast<long long>(C) + 1) + len;
-        kmean[q] = deg > 0 ? (sum * 64) / deg : static_cast<long long>(C) * 64;
-      }
-    }
-    std::vector<int> by_min(pt_perm), by_mean(pt_perm);
-    std::stable_sort(by_min.begin(), by_min.end(), [&](int a, int b) { return karc[a] < karc[b]; });
-    std::stable_sort(by_mean.begin(), by_mean.end(), [&](int a, int b) { return kmean[a] < kmean[b]; });
-    const long m_min = metric(by_min), m_mean = metric(by_mean);
-    const long best = std::min(m_min, m_mean);
-    if (dev_env("B200_KEEP_ORDER") == nullptr && static_cast<double>(m_id) > 1.10 * static_cast<double>(best)) {
-      pt_perm = (m_min <= m_mean) ? by_min : by_mean;
-      identity_order = false;
-    }
-    if (getenv("B200_VERBOSE") != nullptr)
-      fprintf(stderr, "[b200ba] point order: distinct cameras per 1/%d of the rows, summed: caller %ld, by camera arc %ld, by mean camera %ld -> %s\n",
-              chunks, m_id, m_min, m_mean, identity_order ? "caller's order kept" : (m_min <= m_mean ? "by camera arc" : "by mean camera"));
-  }
+  // ---- Internal point order (choose_point_order above): private to the library, undone at the ABI boundary.
+  std::vector<int> pt_perm;   // internal point k = caller point pt_perm[k]
+  long order_metrics[4];
+  const int order_choice = dev_env("B200_KEEP_ORDER") != nullptr
+                               ? (pt_perm.resize(static_cast<size_t>(P)), std::iota(pt_perm.begin(), pt_perm.end(), 0), 0)
+                               : choose_point_order(C, P, N, desc->cam_idx, caller_ptr.data(), prop.multiProcessorCount, &pt_perm, order_metrics);
+  const bool identity_order = order_choice == 0;
+  if (getenv("B200_VERBOSE") != nullptr && dev_env("B200_KEEP_ORDER") == nullptr)
+    fprintf(stderr, "[b200ba] point order: distinct cameras per 1/%d of the rows, summed: caller %ld, by camera arc %ld, by mean camera %ld, by smallest camera %ld -> %s\n",
+            prop.multiProcessorCount, order_metrics[0], order_metrics[1], order_metrics[2], order_metrics[3], kOrderNames[order_choice]);
   // internal copies of the row structure
   std::vector<int> cam_i(static_cast<size_t>(N)), pt_i(static_cast<size_t>(N)), row_perm(static_cast<size_t>(N));
   std::vector<double> obs_i(2 * static_cast<size_t>(N));

@@ -76,6 +76,12 @@ typedef struct b200_ba_desc {
   const void* nccl_unique_id;
 } b200_ba_desc;
 
+/* The point order the library would keep privately for this structure (b200_create re-orders points -- with all their rows --
+ * so that neighbouring points see the same few cameras, and undoes the permutation at every entry point: the layout above is
+ * what the caller sees).  Host-only, needs no GPU: perm_out[k] = caller's e block at internal position k ([P], may be NULL);
+ * metrics_out = distinct cameras per 1/num_chunks of the rows, summed, for {caller's order, by camera arc, by mean camera,
+ * by smallest camera}; *choice_out = which of the four was taken (0 = the caller's order is kept). */
+int b200_plan_point_order(const b200_ba_desc* desc, int num_chunks, int32_t* perm_out, int64_t metrics_out[4], int* choice_out);
 int b200_nccl_unique_id(void* out128);
 int b200_create(const b200_ba_desc* desc, b200_handle** out);
 void b200_destroy(b200_handle* h);

@@ -210,3 +210,41 @@ def test_reduced_program_invariants_on_random_structures(seed, tmp_path):
             sizes.append(rhi - rlo)
         assert covered_pts == rp.P and covered_rows == rp.N
         assert max(sizes) - min(sizes) <= 2 * deg.max() + rp.N // world
+
+
+def test_internal_point_order_plan():
+    """b200_plan_point_order (host-only part of b200_create): the chosen order is a permutation, its score is what numpy
+    computes for it, a capture whose points already follow the frames keeps the caller's order, the SURVEY 8d I2 recipe
+    (points in random order) is re-ordered to a several times better score."""
+    import ceres_solver_b200 as cs
+    from ceres_solver_b200 import bal as B
+
+    def score(cam, pt, P, C, order, chunks):
+        newid = np.empty(P, dtype=np.int64)
+        newid[order] = np.arange(P)
+        rows = np.argsort(newid[pt], kind="stable")
+        deg = np.bincount(pt, minlength=P)
+        # chunk of a row = chunk of the point it belongs to: a point moves to the next chunk once the rows before it reach
+        # chunk * (N / chunks + 1)  (same rule as the library)
+        N = len(cam)
+        target = N // chunks + 1
+        ends = np.cumsum(deg[order])                  # rows up to and including each point, in the new order
+        starts = ends - deg[order]
+        chunk_of_point = starts // target
+        chunk_of_row = np.repeat(chunk_of_point, deg[order])
+        return int(np.unique(chunk_of_row * C + cam[rows]).size)
+
+    for bal, expect_identity in ((B.synthetic_sequence(300, 9000, 40000, seed=3), True), (B.synthetic("tiny"), None)):
+        rp = B.ReducedProgram(bal)
+        perm, metrics, choice = cs.plan_point_order(rp.C, rp.P, rp.row_cam, rp.row_pt, 148)
+        assert sorted(perm.tolist()) == list(range(rp.P))
+        if expect_identity:
+            assert choice == 0 and np.array_equal(perm, np.arange(rp.P))
+        assert metrics[0] == score(rp.row_cam.astype(np.int64), rp.row_pt.astype(np.int64), rp.P, rp.C, np.arange(rp.P), 148)
+    bal = B.synthetic_bal(400, 12000, 52000, seed=11)   # points in random order
+    rp = B.ReducedProgram(bal)
+    perm, metrics, choice = cs.plan_point_order(rp.C, rp.P, rp.row_cam, rp.row_pt, 148)
+    assert choice != 0 and sorted(perm.tolist()) == list(range(rp.P))
+    assert metrics[choice] * 2 < metrics[0]
+    assert metrics[choice] == score(rp.row_cam.astype(np.int64), rp.row_pt.astype(np.int64), rp.P, rp.C, perm.astype(np.int64), 148)
+    assert metrics[choice] == min(metrics[1:])
