@@ -311,8 +311,7 @@ def main():
     single = world == 1
     if args.warmup > 0:
         timed_solve(args.warmup, False)
-        if single:
-            timed_solve(min(args.warmup, 2), True)
+        timed_solve(min(args.warmup, 2), True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     gpu.stats_reset()
@@ -320,11 +319,10 @@ def main():
     launches = gpu.total_launches()
     clocks = sampler.stop()
     iters = max(1, len(recs) - 1)
-    # end to end through the host-buffer boundary
-    # (N > 1: the sharded problem has no host-buffer boundary; end to end is then the device-resident loop with
-    #  the state uploaded from / downloaded to host memory inside the timed call, wall clock, max over ranks)
+    # end to end through the host-buffer boundary (N > 1: every rank drives its shard through the same entry points with its
+    # own host buffers; the few host-side scalars of the loop are combined across ranks; wall clock, max over ranks)
     gpu.stats_reset()
-    e2e_dev_s, e2e_wall_s, recs_e2e = timed_solve(args.steps, single)
+    e2e_dev_s, e2e_wall_s, recs_e2e = timed_solve(args.steps, True)
     h2d, d2h = gpu.transfer_bytes()
     e2e_iters = max(1, len(recs_e2e) - 1)
     # per-kernel event timing for the roofline (same steps, instrumented)

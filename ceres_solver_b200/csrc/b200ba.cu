@@ -1111,6 +1111,26 @@ int pcg_general_dev(b200_handle* h, const b200_solver_options* o) {
   return B200_OK;
 }
 
+// Host scalars of the host-boundary LM loop on a sharded problem: vals[i] is combined across ranks (sum, or max where bit i
+// of max_mask is set) through a few device words and NCCL; a no-op on one GPU.
+int host_allreduce(b200_handle* h, double* vals, int n, unsigned max_mask) {
+#ifdef B200_WITH_NCCL
+  if (h->world <= 1) return B200_OK;
+  CU(cudaMemcpyAsync(h->d_scalars + 16, vals, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  for (int i = 0; i < n; ++i) {
+    const ncclRedOp_t op = ((max_mask >> i) & 1u) ? ncclMax : ncclSum;
+    ncclResult_t r = g_nccl.AllReduce(h->d_scalars + 16 + i, h->d_scalars + 16 + i, 1, ncclDouble, op, h->comm, h->stream);
+    if (r != ncclSuccess) return fail(B200_ERR_NCCL, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+  }
+  CU(cudaMemcpyAsync(h->h_scalars + 16, h->d_scalars + 16, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i) vals[i] = h->h_scalars[16 + i];
+#else
+  (void)h; (void)vals; (void)n; (void)max_mask;
+#endif
+  return B200_OK;
+}
+
 // Reduction over a [points | cameras] vector when the points are sharded across ranks and the cameras are
 // replicated: the point range is reduced locally and combined across ranks, the camera range is counted once.
 // run(offset, count) must launch the partial-producing kernel on that sub-range with `grid` blocks.
@@ -2414,8 +2434,6 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
     return fail(B200_ERR_INVALID_ARGUMENT, "null argument");
   CU(cudaSetDevice(h->device));
   *num_records = 0;
-  if (host_boundary && h->world > 1)
-    return fail(B200_ERR_UNSUPPORTED, "the host-buffer boundary is single-GPU; sharded problems run the device-resident loop");
   const int np = h->np;
   const size_t nr = 2 * static_cast<size_t>(h->N);
   const size_t off = 3 * static_cast<size_t>(h->P);
@@ -2459,10 +2477,21 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
       }
       double mx = 0, sq = 0;
       const double* gr = gradient.data();
+      const int np_local = h->world > 1 ? static_cast<int>(off) : np;   // sharded: points are this rank's, cameras replicated
 #pragma omp parallel for num_threads(kHostThreads) schedule(static) reduction(max : mx) reduction(+ : sq)
-      for (int i = 0; i < np; ++i) {
+      for (int i = 0; i < np_local; ++i) {
         mx = std::max(mx, std::fabs(gr[i]));
         sq += gr[i] * gr[i];
+      }
+      if (h->world > 1) {
+        double v[2] = {mx, sq};
+        OK(host_allreduce(h, v, 2, 0x1u));
+        mx = v[0];
+        sq = v[1];
+        for (int i = np_local; i < np; ++i) {   // the camera part, counted once
+          mx = std::max(mx, std::fabs(gr[i]));
+          sq += gr[i] * gr[i];
+        }
       }
       it.gradient_max_norm = mx;
       it.gradient_norm = std::sqrt(sq);
@@ -2552,16 +2581,33 @@ int b200_lm_solve(b200_handle* h, const b200_lm_options* opt, double* state_inou
         double acc_x = 0.0, acc_s = 0.0, bad = 0.0;
         const double *sl = sol.data(), *xx = x.data(), *sc = scaling.data();
         double *stp = step.data(), *cd = cand.data();
-#pragma omp parallel for num_threads(kHostThreads) schedule(static) reduction(+ : acc_x, acc_s, bad)
+        double cam_x = 0.0, cam_s = 0.0;   // camera part (replicated when sharded: counted once)
+        const int np_local = h->world > 1 ? static_cast<int>(off) : np;
+#pragma omp parallel for num_threads(kHostThreads) schedule(static) reduction(+ : acc_x, acc_s, bad, cam_x, cam_s)
         for (int i = 0; i < np; ++i) {
           const double si = -sl[i];
           stp[i] = si;
           const double ci = xx[i] + si * sc[i];
           cd[i] = ci;
-          acc_x += xx[i] * xx[i];
-          acc_s += (xx[i] - ci) * (xx[i] - ci);
+          const double ax = xx[i] * xx[i], as = (xx[i] - ci) * (xx[i] - ci);
+          if (i < np_local) {
+            acc_x += ax;
+            acc_s += as;
+          } else {
+            cam_x += ax;
+            cam_s += as;
+          }
           bad += (si - si);  // NaN/Inf - itself is NaN, finite - itself is 0
         }
+        if (h->world > 1) {
+          double v[3] = {acc_x, acc_s, bad};
+          OK(host_allreduce(h, v, 3, 0u));
+          acc_x = v[0];
+          acc_s = v[1];
+          bad = v[2];
+        }
+        acc_x += cam_x;
+        acc_s += cam_s;
         step_finite = (bad == 0.0);
         host_x_sq = acc_x;
         host_step_sq = acc_s;

@@ -54,6 +54,7 @@ def main():
     xj = np.concatenate([xfull[3 * plo:3 * phi], xfull[3 * rp.P:]])
     jtj = gpu.jtj_multiply(xj, D)
     _, recs = gpu.lm_solve(state, gpu.lm_options(max_num_iterations=3))
+    _, recs_hb = gpu.lm_solve(state, gpu.lm_options(max_num_iterations=3), host_boundary=True)   # through the host buffers
     gpu.close()
 
     failures = []
@@ -93,6 +94,14 @@ def main():
         o.num_threads = po.max_threads()
         o.max_num_iterations = 3
         _, recs_o, _ = orc.solve(full, o)
+        for a, b in zip(recs_hb, recs):
+            for key in ("cost", "step_norm", "gradient_max_norm", "tr_radius"):
+                if abs(a[key] - b[key]) > 1e-6 * max(abs(b[key]), 1e-300):
+                    failures.append("host-boundary iteration %d %s: %r vs %r" % (a["iteration"], key, a[key], b[key]))
+            if a["ls_iterations"] != b["ls_iterations"]:
+                failures.append("host-boundary iteration %d CG iterations %d vs %d" % (a["iteration"], a["ls_iterations"], b["ls_iterations"]))
+        if len(recs_hb) != len(recs):
+            failures.append("host-boundary trace length %d vs %d" % (len(recs_hb), len(recs)))
         if not (len(recs) == len(recs1) == len(recs_o)):
             failures.append("trace lengths %d %d %d" % (len(recs), len(recs1), len(recs_o)))
         else:
