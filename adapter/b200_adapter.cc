@@ -76,15 +76,12 @@ std::unique_ptr<Evaluator> B200Evaluator::Create(const Evaluator::Options& optio
         *error = "B200Evaluator: only the trivial and Huber losses are implemented";
         return nullptr;
       }
-      // HuberLoss(a): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond (loss_function.cc:52-66); two probes deep in the
-      // outlier region recover a whatever its magnitude: rho(4 s) - 2 rho(s) = a^2 there
-      double r1[3], r4[3];
-      double s_probe = 1e30;
-      loss->Evaluate(s_probe, r1);
-      loss->Evaluate(4.0 * s_probe, r4);
       this_type = B200_LOSS_HUBER;
-      this_a = std::sqrt(r4[0] - 2.0 * r1[0]);
-      if (!(this_a > 0.0) || !std::isfinite(this_a)) this_a = r1[1] * std::sqrt(s_probe);   // rho' = a / sqrt(s)
+      this_a = B200HuberScale(*loss);
+      if (!std::isfinite(this_a)) {
+        *error = "B200Evaluator: HuberLoss scale of residual block " + std::to_string(i) + " could not be recovered";
+        return nullptr;
+      }
     }
     if (i == 0) {
       loss_type = this_type;
@@ -187,7 +184,12 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
   }
   summary.num_iterations = s.num_iterations;
   summary.residual_norm = s.residual_norm;
-  summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);  // same numeric order
+  static_assert(static_cast<int>(LinearSolverTerminationType::SUCCESS) == B200_LS_SUCCESS &&
+                    static_cast<int>(LinearSolverTerminationType::NO_CONVERGENCE) == B200_LS_NO_CONVERGENCE &&
+                    static_cast<int>(LinearSolverTerminationType::FAILURE) == B200_LS_FAILURE &&
+                    static_cast<int>(LinearSolverTerminationType::FATAL_ERROR) == B200_LS_FATAL_ERROR,
+                "b200ba.h numbers the termination types like linear_solver.h:57-74");
+  summary.termination_type = static_cast<LinearSolverTerminationType>(s.termination_type);
   return summary;
 }
 

@@ -20,6 +20,8 @@
 #ifndef CERES_INTERNAL_B200_ADAPTER_H_
 #define CERES_INTERNAL_B200_ADAPTER_H_
 
+#include <cmath>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -28,6 +30,7 @@
 #include "ceres/evaluator.h"
 #include "ceres/execution_summary.h"
 #include "ceres/linear_solver.h"
+#include "ceres/loss_function.h"
 #include "ceres/program.h"
 
 namespace ceres::internal {
@@ -35,6 +38,19 @@ namespace ceres::internal {
 // The one predicate both factory hunks use, so that the evaluator and the linear solver are always selected together.
 inline bool B200Selected(LinearSolverType linear_solver_type, SparseLinearAlgebraLibraryType sparse_library) {
   return linear_solver_type == ITERATIVE_SCHUR && sparse_library == CUDA_SPARSE;
+}
+
+// The scale a of a HuberLoss (its members are private).  Beyond s = a^2 the loss is 2 a sqrt(s) - a^2 with
+// rho'(s) = a / sqrt(s) (loss_function.cc:52-66): probed at s = 2^200, whose square root is the exact power 2^100, the
+// product rho'(s) * 2^100 returns a to the last bit for every a < 2^100 (the difference rho(4s) - 2 rho(s) = a^2 would
+// cancel: 6e-6 relative error at a = 3e4).  A loss that is still in its inlier region there (rho' = 1) has no usable
+// scale: HUGE_VAL, which B200Evaluator::Create refuses.
+inline double B200HuberScale(const LossFunction& loss) {
+  const double root = std::ldexp(1.0, 100);
+  double rho[3];
+  loss.Evaluate(root * root, rho);
+  if (rho[1] >= 1.0 || !(rho[1] > 0.0)) return HUGE_VAL;
+  return rho[1] * root;
 }
 
 // Shared owner of the device problem; evaluator, Jacobian and linear solver all point at it.

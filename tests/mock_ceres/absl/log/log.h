@@ -1,0 +1,2 @@
+// test mock: see ceres/mock_all.h
+#include "../../ceres/mock_all.h"
