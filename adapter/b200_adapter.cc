@@ -154,6 +154,13 @@ LinearSolver::Summary B200IterativeSchurSolver::SolveImpl(BlockSparseMatrix* A, 
     summary.message = "B200IterativeSchurSolver needs the Jacobian created by B200Evaluator.";
     return summary;
   }
+  if (options_.use_explicit_schur_complement) {
+    // Evaluator::Options carries no such flag, so the evaluator factory cannot opt out for it: refuse loudly here rather
+    // than hand a Jacobian whose values live in HBM to SparseSchurComplementSolver
+    summary.termination_type = LinearSolverTerminationType::FATAL_ERROR;
+    summary.message = "use_explicit_schur_complement is not available on the B200 path (the Schur complement stays implicit).";
+    return summary;
+  }
   b200_solver_options o;
   b200_solver_options_default(&o);
   switch (options_.preconditioner_type) {
